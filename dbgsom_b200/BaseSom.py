@@ -1,0 +1,389 @@
+"""Host driver of the B200 batch-SOM: same estimator surface as the reference's `BaseSom`.
+
+Mirrors `dbgsom/BaseSom.py` of SandroMartens/DBGSOM at the API level (constructor
+keywords :42-80, `fit` :88-131, fitted attributes, `transform`, metrics) while the numeric
+epoch (:394-407) runs on the GPU through `dbgsom_b200.engine.DeviceEngine` (ctypes ->
+`libdbgsom_b200.so`, hand-written sm_100a kernels).  There is no CPU fallback: without the
+CUDA library and a device, `fit` raises.
+
+What stays on the host, as in the reference: the growing-map logic (`topology.py`), the
+sigma schedule, thresholds, early stopping, and the fitted NetworkX graph `som_`.
+"""
+
+from __future__ import annotations
+
+from math import exp, log, pi, sqrt
+from typing import Any
+
+import numpy as np
+from sklearn.base import BaseEstimator
+from sklearn.utils import check_array, check_random_state
+from sklearn.utils.validation import check_is_fitted
+
+from .topology import MapTopology
+
+__all__ = ["BaseSom", "sigma_linear", "sigma_exponential"]
+
+
+def sigma_linear(sigma_start, sigma_end, max_iter, current_iter, learning_rate=None):
+    """Same contract as `linear_decay`, dbgsom/BaseSom.py:1001-1012."""
+    frac = current_iter / max_iter
+    return sigma_start * (1 - frac) + sigma_end * frac
+
+
+def sigma_exponential(sigma_start, sigma_end, max_iter, current_iter, learning_rate):
+    """Same contract as `exponential_decay`, dbgsom/BaseSom.py:1015-1025."""
+    return sigma_end + (sigma_start - sigma_end) * exp(-learning_rate * current_iter)
+
+
+class BaseSom(BaseEstimator):
+    """Shared training driver of `SomVQ` and `SomClassifier`.
+
+    Hyper-parameters are those of the reference (same names, defaults and meaning,
+    including the spelling `convergence_treshold`); the trailing ones are additions:
+
+    device : str, default "cuda"
+        CUDA device the epoch kernels run on.
+    compat_pack_rows : bool, default True
+        Reproduce the reference's packed centre rows.  False gives
+        the index-aligned batch update.
+    bmu_backend : {"auto", "tensor", "simt"}, default "auto"
+        "tensor" = tcgen05 fp16 candidate search + exact re-score, "simt" = fp32 CUDA-core
+        candidate search + exact re-score.  Both return the same winners.
+    distributed : bool, default False
+        SPMD multi-GPU: every rank calls `fit` with its own shard of the samples; only the
+        per-neuron partial sums are all-reduced each epoch (`torch.distributed`, NCCL).
+    """
+
+    def __init__(
+        self,
+        n_iter: int = 200,
+        convergence_iter: int = 1,
+        spreading_factor: float = 0.5,
+        sigma_start: float | None = None,
+        sigma_end: float | None = None,
+        vertical_growth: bool = False,
+        decay_function: str = "exponential",
+        learning_rate: float = 0.02,
+        verbose: bool = False,
+        coarse_training_frac: float = 0.5,
+        random_state: Any = None,
+        convergence_treshold: float = 10**-5,
+        max_neurons: int = 100,
+        metric: str = "euclidean",
+        threshold_method: str = "se",
+        growth_criterion: str = "quantization_error",
+        min_samples_vertical_growth: int = 100,
+        n_jobs: int = 1,
+        device: str = "cuda",
+        compat_pack_rows: bool = True,
+        bmu_backend: str = "auto",
+        distributed: bool = False,
+    ) -> None:
+        self.spreading_factor = spreading_factor
+        self.n_iter = n_iter
+        self.convergence_iter = convergence_iter
+        self.sigma_start = sigma_start
+        self.sigma_end = sigma_end
+        self.decay_function = decay_function
+        self.learning_rate = learning_rate
+        self.verbose = verbose
+        self.coarse_training_frac = coarse_training_frac
+        self.random_state = random_state
+        self.convergence_treshold = convergence_treshold
+        self.max_neurons = max_neurons
+        self.metric = metric
+        self.threshold_method = threshold_method
+        self.growth_criterion = growth_criterion
+        self.min_samples_vertical_growth = min_samples_vertical_growth
+        self.vertical_growth = vertical_growth
+        self.n_jobs = n_jobs
+        self.device = device
+        self.compat_pack_rows = compat_pack_rows
+        self.bmu_backend = bmu_backend
+        self.distributed = distributed
+
+    # ------------------------------------------------------------------ hooks for subclasses
+    def _check_input_data(self, X, y):
+        raise NotImplementedError
+
+    def _label_prototypes(self, winners: np.ndarray, y, engine) -> None:
+        raise NotImplementedError
+
+    def _fit(self, winners: np.ndarray) -> None:
+        pass
+
+    def predict(self, X):
+        raise NotImplementedError
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _make_engine(self, distributed: bool | None = None):
+        """Create the device engine (the only place one is made).
+
+        CPU-only unit tests of the host logic replace this factory with a checker; the
+        product path has no alternative to the CUDA engine.
+        """
+        from .engine import DeviceEngine
+
+        return DeviceEngine(
+            device=self.device,
+            bmu_backend=self.bmu_backend,
+            distributed=self.distributed if distributed is None else distributed,
+        )
+
+    def _check_arguments(self) -> None:
+        # The reference declares these checks (dbgsom/BaseSom.py:143-155) but never calls
+        # them; invalid values would fail later with obscure errors, so they are enforced.
+        if self.decay_function not in ("linear", "exponential"):
+            raise ValueError("Decay function not supported. Must be 'linear' or 'exponential'.")
+        if self.threshold_method not in ("se", "classical"):
+            raise ValueError("threshold_method not supported. Must be 'se' or 'classical'.")
+        if self.growth_criterion not in ("quantization_error", "entropy"):
+            raise ValueError("growth_criterion not supported. Must be 'quantization_error' or 'entropy'.")
+        if self.vertical_growth:
+            # The reference's vertical growth raises TypeError on every call (quirk Q11).
+            raise NotImplementedError("vertical_growth is not supported (broken in the reference, out of scope)")
+
+    # ------------------------------------------------------------------ fit
+    def fit(self, X, y=None):
+        """Train the map on X (and y).  Same contract as dbgsom/BaseSom.py:88-131."""
+        self._check_arguments()
+        X, y = self._check_input_data(X, y)
+        if y is not None:
+            classes, y = np.unique(y, return_inverse=True)
+            self.classes_ = np.array(classes)
+        self.random_state_ = check_random_state(self.random_state)
+        engine = self._make_engine()
+        try:
+            self._initialize_som(engine, X, y)
+            self._grow_som(engine)
+            self._finalize(engine, y)
+        finally:
+            engine.close()
+        self.n_features_in_ = X.shape[1]
+        self.n_iter_ = self._current_epoch
+        return self
+
+    def _initialize_som(self, engine, X: np.ndarray, y) -> None:
+        """`_initialize_som` + `_create_som`, dbgsom/BaseSom.py:352-369, :419-444."""
+        self._current_epoch = 0
+        self.converged_ = False
+        self._training_phase = "coarse"
+        self._neurons_added = True
+        n_classes = len(self.classes_) if y is not None else 0
+        stats = engine.load_data(X, y, n_classes)
+        self._total_variance = stats["total_variance"]
+        self.growing_threshold_ = self._growing_threshold(stats, X.shape[1])
+        # identical draw to `rng.choice(a=data, size=4, replace=False)` (row choice)
+        rng = np.random.default_rng(seed=self.random_state)
+        rows = rng.choice(stats["n_samples"], size=4, replace=False)
+        self._topology = MapTopology.initial_square()
+        engine.init_map_from_rows(rows, capacity=self._capacity_hint())
+        self._hops_dirty = True
+
+    def _capacity_hint(self) -> int:
+        # growth is only tested before a growth step (quirk Q8) so the map can overshoot
+        # max_neurons by up to one boundary ring; the engine re-allocates if exceeded.
+        return int(max(16, 2 * self.max_neurons + 64))
+
+    def _growing_threshold(self, stats: dict, n_dim: int) -> float:
+        """`_calculate_growing_threshold`, dbgsom/BaseSom.py:371-385."""
+        if self.growth_criterion == "entropy":
+            return self.spreading_factor
+        if self.threshold_method == "classical":
+            return -n_dim * log(self.spreading_factor)
+        return float(150 * -log(self.spreading_factor) * stats["std_norm"])
+
+    def _current_sigma(self) -> float:
+        """`_calculate_current_sigma`, dbgsom/BaseSom.py:863-902."""
+        m = len(self._topology)
+        start = 0.2 * sqrt(m) if self.sigma_start is None else self.sigma_start
+        end = max(0.7, 0.05 * sqrt(m)) if self.sigma_end is None else self.sigma_end
+        if self._training_phase != "coarse":
+            return end
+        decay = sigma_linear if self.decay_function == "linear" else sigma_exponential
+        return decay(
+            sigma_start=start,
+            sigma_end=end,
+            max_iter=self.n_iter,
+            current_iter=self._current_epoch / self.coarse_training_frac,
+            learning_rate=self.learning_rate,
+        )
+
+    def _grow_som(self, engine) -> None:
+        """Epoch loop -- dbgsom/BaseSom.py:387-417."""
+        topo = self._topology
+        epochs = range(self.n_iter)
+        if self.verbose:
+            from tqdm import tqdm
+
+            epochs = tqdm(epochs, unit=" epochs")
+        use_entropy = self.growth_criterion == "entropy"
+        for epoch in epochs:
+            self._current_epoch = epoch
+            if epoch > self.coarse_training_frac * self.n_iter:
+                self._training_phase = "fine"
+            if self._hops_dirty:
+                # the reference recomputes all-pairs hops every epoch (quirk Q3); they only
+                # change when the map grew
+                engine.set_hops(topo.hop_matrix_u16())
+                self._hops_dirty = False
+            result = engine.epoch(
+                sigma=self._current_sigma(),
+                pack_rows=self.compat_pack_rows,
+                entropy_error=use_entropy,
+            )
+            topo.error[:] = result["error"]
+            if result["change"] < self.convergence_treshold:
+                self.converged_ = True  # a latch, like the reference (quirk Q7)
+            if self.converged_ and self._training_phase == "fine":
+                break
+            if (
+                self._training_phase == "coarse"
+                and len(topo) < self.max_neurons
+                and epoch % self.convergence_iter == self.convergence_iter - 1
+            ):
+                topo.distribute_errors(self.growing_threshold_)
+                ops = topo.grow(self.growing_threshold_, epoch)
+                if ops:
+                    engine.apply_row_ops(ops, n_rows=len(topo))
+                    self._hops_dirty = True
+
+    # ------------------------------------------------------------------ after the loop
+    def _finalize(self, engine, y) -> None:
+        """Everything `fit` does after `_grow_som` (dbgsom/BaseSom.py:116-127).
+
+        The reference runs four to five separate BMU passes here (topographic error,
+        quantisation error, node statistics, classifier labelling, `labels_`); two passes on
+        the device feed all of them (a top-2 pass on the pre-update prototypes, a top-1 pass
+        on the final reduced map).
+        """
+        topo = self._topology
+        # Quirk kept for parity: after the loop the reference's `weights_` / `neurons_` still
+        # hold the state from the START of the last epoch (they are refreshed at the top of
+        # the loop body, dbgsom/BaseSom.py:397-401), so topographic error, quantisation
+        # error and node statistics are measured against the prototypes BEFORE the final
+        # update, while the graph (and the final `weights_`) carry the updated ones.
+        dist2, idx2 = engine.bmu_train(n_bmu=2, previous=True)
+        m_stats = engine.n_previous_rows
+        winners, dist = idx2[:, 0], dist2[:, 0]
+        n_total = engine.n_samples_global
+
+        # topographic error: grid distance of the two BMUs > 1.5 (dbgsom/BaseSom.py:924-953)
+        pos = topo.positions().astype(np.float64)
+        sep = pos[idx2[:, 0]] - pos[idx2[:, 1]]
+        te_count = float(np.count_nonzero(np.sqrt((sep * sep).sum(axis=1)) > 1.5))
+        qe_sum = float(dist.sum())
+        te_count, qe_sum = engine.allreduce_scalars([te_count, qe_sum])
+        self.topographic_error_ = te_count / n_total
+        self.quantization_error_ = qe_sum / n_total
+
+        # node statistics (dbgsom/BaseSom.py:181-221)
+        m = len(topo)
+        if m_stats != m:
+            raise RuntimeError(
+                "the map grew in the final epoch (coarse_training_frac >= 1); the reference "
+                "fails in this configuration as well (hit_count missing on the new nodes)"
+            )
+        weights = engine.weights()
+        avg_dist = _u_matrix(weights, topo)
+        bandwidth = avg_dist.mean()
+        hits = np.bincount(winners, minlength=m).astype(np.float64)
+        kern = np.exp(-(dist**2) / (2 * bandwidth**2)) / (bandwidth * sqrt(2 * pi))
+        dens_sum = np.bincount(winners, weights=kern, minlength=m)
+        hits, dens_sum = engine.allreduce_arrays([hits, dens_sum])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            density = np.where(hits > 0, dens_sum / hits, 0.0)
+
+        # neurons without samples leave the map (dbgsom/BaseSom.py:223-235)
+        dead = np.flatnonzero(hits == 0)
+        alive = np.flatnonzero(hits > 0)
+        attrs = {
+            "weight": list(weights),
+            "density": list(density),
+            "hit_count": list(hits),
+            "average_distance": list(avg_dist),
+        }
+        graph = topo.to_networkx(attrs)
+        graph.remove_nodes_from([topo.pos[i] for i in dead])
+        self.som_ = graph
+        self._topology = topo.without(dead)
+        self.neurons_ = list(graph.nodes)
+        self.weights_ = weights[alive]
+        self._distance_matrix = self._topology.hop_matrix()
+
+        # prototype labels and `labels_` use the UPDATED, reduced map (dbgsom/BaseSom.py:121,
+        # :127; SomVQ.py:150-152; SomClassifier.py:130-152): one more BMU pass
+        engine.keep_rows(alive)
+        _, idx1 = engine.bmu_train(n_bmu=1)
+        train_winners = idx1[:, 0]
+        self._label_prototypes(train_winners, y, engine)
+        self._fit(train_winners)
+
+    # ------------------------------------------------------------------ inference helpers
+    def _get_winning_neurons(self, data, n_bmu: int):
+        """Distances and indices of the `n_bmu` best matching prototypes per sample.
+
+        Same return shapes as dbgsom/BaseSom.py:446-464; computed on the device.
+        """
+        engine = self._make_engine(distributed=False)
+        try:
+            dist, idx = engine.bmu(np.asarray(data), self.weights_, n_bmu)
+        finally:
+            engine.close()
+        if n_bmu == 1:
+            return dist.reshape(-1), idx.reshape(-1)
+        return dist, idx
+
+    def _extract_values_from_graph(self, attribute: str) -> np.ndarray:
+        """Node attribute as an array in node order (dbgsom/BaseSom.py:237-239)."""
+        return np.array([data[attribute] for _, data in self.som_.nodes.data()])
+
+    def calculate_quantization_error(self, X) -> float:
+        """Mean distance to the nearest prototype (dbgsom/BaseSom.py:904-922)."""
+        check_is_fitted(self)
+        X = check_array(X)
+        dist, _ = self._get_winning_neurons(X, n_bmu=1)
+        return float(np.mean(dist))
+
+    def transform(self, X, y=None) -> np.ndarray:
+        """Non-negative sparse code of each sample over the normalised prototypes.
+
+        Host path, identical to dbgsom/BaseSom.py:241-268 (scikit-learn `SparseCoder`,
+        LARS); not part of the training epoch.
+        """
+        from sklearn.decomposition import SparseCoder
+        from sklearn.preprocessing import normalize
+
+        check_is_fitted(self)
+        X = check_array(X, dtype=[np.float64, np.float32])
+        coder = SparseCoder(
+            dictionary=normalize(self.weights_),
+            n_jobs=self.n_jobs,
+            positive_code=True,
+            transform_alpha=0,
+            transform_algorithm="lasso_lars",
+        )
+        return coder.transform(normalize(X))
+
+
+def _u_matrix(weights: np.ndarray, topo: MapTopology) -> np.ndarray:
+    """Mean input-space distance of each prototype to ALL adjacency entries of the map.
+
+    The reference averages over the neighbour lists of the whole graph, not over each
+    node's own neighbours (`_get_u_matrix`, dbgsom/BaseSom.py:320-337, quirk Q12), i.e. a
+    degree-weighted mean distance to every prototype.
+    """
+    from scipy.spatial.distance import cdist
+
+    m = len(topo)
+    deg = np.array([len(a) for a in topo.adj], dtype=np.float64)
+    total = deg.sum()
+    if total == 0:
+        return np.full(m, np.nan)
+    out = np.empty(m)
+    step = max(1, int(2**24 // max(m, 1)))
+    for s in range(0, m, step):
+        d = cdist(weights[s : s + step], weights)
+        out[s : s + step] = (d * deg[None, :]).sum(axis=1) / total
+    return out

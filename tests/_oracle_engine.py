@@ -1,0 +1,87 @@
+"""TEST-ONLY engine: drives the host estimator logic with the CPU oracle.
+
+Implements the interface of `dbgsom_b200.engine.DeviceEngine` in numpy float64 on top of
+`oracle.som_oracle`, so the `-m "not gpu"` suite can check growth rules, schedules and
+fitted attributes against the reference's trajectory fixtures without a GPU.  It lives
+under tests/ on purpose: the product package never imports the oracle.
+"""
+import numpy as np
+
+from dbgsom_b200.hostmath import class_entropy
+from dbgsom_b200.topology import HOP_INF
+from oracle import som_oracle as O
+
+
+class OracleEngine:
+    sample_offset = 0
+
+    def __init__(self, **_):
+        self.epochs = 0
+
+    def load_data(self, X, y, n_classes):
+        self.X, self.y, self.n_classes = X, y, n_classes
+        self.n_samples_global = X.shape[0]
+        self.total_var = O.total_variance(X)
+        std = np.std(X, axis=0, ddof=1)
+        return {
+            "n_samples": X.shape[0],
+            "total_variance": self.total_var,
+            "std_norm": np.linalg.norm(std),
+        }
+
+    def init_map_from_rows(self, rows, capacity):
+        self.W = np.array(self.X[np.asarray(rows)], dtype=self.X.dtype)
+
+    def set_hops(self, hop_u16):
+        hop = hop_u16.astype(np.float64)
+        hop[hop_u16 == HOP_INF] = np.inf
+        self.hop = hop
+
+    def epoch(self, sigma, pack_rows, entropy_error):
+        out = O.epoch_step(self.X, self.W, self.hop, sigma, self.total_var, pack=pack_rows)
+        self.W_prev = self.W
+        self.W = out["W_new"]
+        self.epochs += 1
+        if entropy_error:
+            m = self.W.shape[0]
+            hist = np.bincount(out["winners"] * self.n_classes + self.y, minlength=m * self.n_classes)
+            err = class_entropy(hist.reshape(m, self.n_classes))
+        else:
+            err = out["E"]
+        return {"error": err, "counts": out["n"], "change": out["change"]}
+
+    def apply_row_ops(self, ops, n_rows):
+        W = np.zeros((n_rows, self.W.shape[1]))
+        W[: self.W.shape[0]] = self.W
+        for op in ops:
+            w = 2 * W[op.a] - W[op.b]
+            if op.c >= 0:
+                w = (w + W[op.c]) / 2
+            W[op.dst] = w
+        self.W = W
+
+    def weights(self):
+        return np.array(self.W, dtype=np.float64)
+
+    @property
+    def n_previous_rows(self):
+        return self.W_prev.shape[0]
+
+    def keep_rows(self, alive):
+        self.W = self.W[alive]
+
+    def bmu_train(self, n_bmu, previous=False):
+        return self.bmu(self.X, self.W_prev if previous else self.W, n_bmu)
+
+    def bmu(self, X, W, n_bmu):
+        dist, idx = O.bmu(X, W, n_bmu)
+        return dist.reshape(X.shape[0], n_bmu), idx.reshape(X.shape[0], n_bmu)
+
+    def allreduce_scalars(self, vals):
+        return list(vals)
+
+    def allreduce_arrays(self, arrs, op="sum"):
+        return list(arrs)
+
+    def close(self):
+        pass

@@ -1,0 +1,459 @@
+// K1 front end on the 5th-generation tensor cores (sm_100a): fp16 tcgen05.mma with TMEM
+// accumulators, operands staged by TMA, candidate tracking fused into the TMEM epilogue.
+//
+// Replaces the distance evaluation inside BaseSom._get_winning_neurons (dbgsom/BaseSom.py:446-464;
+// the reference runs sklearn's float64 GEMM expansion ||x||^2 - 2 x.w + ||w||^2).  Here the score
+// of prototype j for sample i is  s_ij = wnorm_j - 2 x'_i . u_j  with the shadows of
+// dbgsom_prepare_x16 / dbgsom_prepare_w (x' centred on the data, u centred on the prototype mean,
+// both scaled by a power of two; s_ij equals the squared distance up to a per-sample constant).
+//   n_pass = 1 :  x'.u ~ xh.uh                          (fp16 inputs, error ~ 2^-9  ||x'|| ||u||)
+//   n_pass = 3 :  x'.u ~ xh.uh + xh.ul + xl.uh          (split fp16,  error ~ 2^-20 ||x'|| ||u||)
+// all products accumulate in one fp32 TMEM tile.  The epilogue never writes the N x M score
+// matrix: each of its 128 threads owns one TMEM lane = one sample row, streams the scores of all
+// M prototypes through RowTracker (common.cuh) and emits at most DBGSOM_MAX_CAND candidates per
+// sample for the exact float64 re-score (bmu_resolve.cu).
+//
+// CTA = 128 sample rows x all prototypes, persistent over row tiles.  Warp roles:
+//   warp 0    TMA producer (one elected lane)
+//   warp 1    MMA issuer   (one elected lane; tcgen05.mma cta_group::1, M=128, N=BN, K=16)
+//   warp 2    TMEM allocate / free
+//   warps 4-7 epilogue: tcgen05.ld 32x32b -> registers -> score -> candidate tracking
+// Pipelines: smem ring full/empty (TMA <-> MMA), TMEM double buffer full/empty (MMA <-> epilogue),
+// and, when the whole K extent of the sample tile fits (XRES), a resident A tile loaded once per
+// row tile so that only prototypes stream from L2.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace dbgsom {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // fp16 elements = one 128-byte swizzle atom row
+constexpr int UMMA_K = 16;
+constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int TC_THREADS = 256;
+constexpr int EPI_WARP0 = 4;
+constexpr int MAX_RES_KB = 4;  // resident A up to D = 256
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, fp16 inputs, fp32 accumulate
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile in shared memory, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart.
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
+// layout SWIZZLE_128B=2 [61,64).)
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=B=f16 (0),
+// both K-major (0), N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t instr_desc_f16(int m, int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------ layout
+template <int NPASS, int BN, bool XRES>
+struct Cfg {
+  static constexpr int NA = NPASS == 3 ? 2 : 1;  // hi (+ lo) tiles per operand
+  static constexpr int B_TILE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = NA * B_TILE_BYTES + (XRES ? 0 : NA * A_TILE_BYTES);
+  static constexpr int RES_BYTES = XRES ? MAX_RES_KB * NA * A_TILE_BYTES : 0;
+  static constexpr int RING_BYTES = BM * kMaxCand * 8;
+  static constexpr int MISC_BYTES = 1024;  // barriers + tmem pointer
+  static constexpr int SMEM_BUDGET = 227 * 1024 - 1024;  // minus alignment slack
+  static constexpr int STAGES_RAW = (SMEM_BUDGET - RES_BYTES - RING_BYTES - MISC_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = RES_BYTES + STAGES * STAGE_BYTES + RING_BYTES + MISC_BYTES + 1024;
+  static constexpr int TMEM_COLS = 2 * BN;  // two accumulator buffers (256 or 512 columns)
+  static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
+};
+
+struct Barriers {
+  uint64_t full[8], empty[8];
+  uint64_t a_full, a_empty;
+  uint64_t tmem_full[2], tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+template <int NPASS, int NB, int BN, bool XRES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    bmu_cand_tensor_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
+                           const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
+                           int64_t N, int KB, int NT, const float* __restrict__ wnorm,
+                           const float* __restrict__ xnorm16, const float* __restrict__ wmax, float bound_coef,
+                           int32_t* __restrict__ idx_out, int32_t* __restrict__ cand_idx,
+                           uint8_t* __restrict__ cand_count) {
+  using C = Cfg<NPASS, BN, XRES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* res_a = smem;                               // [kb][hi|lo] A tiles (XRES)
+  uint8_t* stages = smem + C::RES_BYTES;               // ring
+  uint8_t* ring = stages + C::STAGES * C::STAGE_BYTES;  // candidate tables
+  Barriers* bars = reinterpret_cast<Barriers*>(ring + C::RING_BYTES);
+  int* ring_idx = reinterpret_cast<int*>(ring);
+  float* ring_val = reinterpret_cast<float*>(ring + BM * kMaxCand * 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t n_row_tiles = ceil_div<int64_t>(N, BM);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_xh);
+    tma_prefetch_desc(&map_wh);
+    if (NPASS == 3) {
+      tma_prefetch_desc(&map_xl);
+      tma_prefetch_desc(&map_wl);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->empty[s], 1);
+    }
+    mbar_init(&bars->a_full, 1);
+    mbar_init(&bars->a_empty, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bars->tmem_full[b], 1);
+      mbar_init(&bars->tmem_empty[b], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
+                 "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0, a_phase = 0;
+      for (int64_t rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x) {
+        const int row0 = (int)(rt * BM);
+        if (XRES) {
+          mbar_wait(&bars->a_empty, a_phase ^ 1);
+          mbar_expect_tx(&bars->a_full, (uint32_t)(KB * C::NA * A_TILE_BYTES));
+          for (int kb = 0; kb < KB; ++kb) {
+            tma_load_2d(res_a + (kb * C::NA + 0) * A_TILE_BYTES, &map_xh, &bars->a_full, kb * BK, row0);
+            if (NPASS == 3) tma_load_2d(res_a + (kb * C::NA + 1) * A_TILE_BYTES, &map_xl, &bars->a_full, kb * BK, row0);
+          }
+          a_phase ^= 1;
+        }
+        for (int nt = 0; nt < NT; ++nt) {
+          for (int kb = 0; kb < KB; ++kb) {
+            mbar_wait(&bars->empty[stage], phase ^ 1);
+            uint8_t* st = stages + stage * C::STAGE_BYTES;
+            mbar_expect_tx(&bars->full[stage], (uint32_t)C::STAGE_BYTES);
+            tma_load_2d(st, &map_wh, &bars->full[stage], kb * BK, nt * BN);
+            if (NPASS == 3) tma_load_2d(st + C::B_TILE_BYTES, &map_wl, &bars->full[stage], kb * BK, nt * BN);
+            if (!XRES) {
+              uint8_t* sa = st + C::NA * C::B_TILE_BYTES;
+              tma_load_2d(sa, &map_xh, &bars->full[stage], kb * BK, row0);
+              if (NPASS == 3) tma_load_2d(sa + A_TILE_BYTES, &map_xl, &bars->full[stage], kb * BK, row0);
+            }
+            if (++stage == C::STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc = instr_desc_f16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0, a_phase = 0, acc = 0, acc_phase = 0;
+      for (int64_t rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x) {
+        if (XRES) {
+          mbar_wait(&bars->a_full, a_phase);
+          a_phase ^= 1;
+        }
+        for (int nt = 0; nt < NT; ++nt) {
+          mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * BN;
+          for (int kb = 0; kb < KB; ++kb) {
+            mbar_wait(&bars->full[stage], phase);
+            tc_fence_after();
+            uint8_t* st = stages + stage * C::STAGE_BYTES;
+            const uint32_t b_hi = smem_u32(st);
+            const uint32_t b_lo = b_hi + C::B_TILE_BYTES;
+            const uint32_t a_hi = XRES ? smem_u32(res_a + kb * C::NA * A_TILE_BYTES)
+                                       : smem_u32(st + C::NA * C::B_TILE_BYTES);
+            const uint32_t a_lo = a_hi + A_TILE_BYTES;
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint32_t koff = k * UMMA_K * 2;  // bytes along K inside the swizzle atom
+              tc_mma_f16(tmem_d, smem_desc_sw128(a_hi + koff), smem_desc_sw128(b_hi + koff), idesc, (kb | k) != 0);
+              if (NPASS == 3) {
+                tc_mma_f16(tmem_d, smem_desc_sw128(a_hi + koff), smem_desc_sw128(b_lo + koff), idesc, 1);
+                tc_mma_f16(tmem_d, smem_desc_sw128(a_lo + koff), smem_desc_sw128(b_hi + koff), idesc, 1);
+              }
+            }
+            tc_commit(&bars->empty[stage]);  // frees the smem stage once these MMAs have read it
+            if (++stage == C::STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          tc_commit(&bars->tmem_full[acc]);  // accumulator complete -> epilogue
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+        }
+        if (XRES) tc_commit(&bars->a_empty);  // resident A tile may be overwritten
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ================================================================ epilogue
+    const int t = threadIdx.x - EPI_WARP0 * 32;  // 0..127 = TMEM lane = row within the tile
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    int* my_idx = ring_idx + t * kMaxCand;
+    float* my_val = ring_val + t * kMaxCand;
+    uint32_t acc = 0, acc_phase = 0;
+    for (int64_t rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x) {
+      const int64_t row = rt * BM + t;
+      RowTracker<NB, false> trk;
+      {
+        CandBound b;
+        b.rel = 0.f;
+        b.abs_d = 0.f;
+        b.abs_s = row < N ? 2.f * tensor_score_bound(xnorm16[row], wmax, bound_coef) : 0.f;
+        trk.init(b);
+      }
+      for (int nt = 0; nt < NT; ++nt) {
+        mbar_wait(&bars->tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + lane_base + acc * BN;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_acc + c0, r);
+          tmem_ld_wait();
+          const int col = nt * BN + c0;
+          const float4* wn4 = reinterpret_cast<const float4*>(wnorm + col);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const float4 wa = __ldg(wn4 + 2 * g), wb = __ldg(wn4 + 2 * g + 1);
+            float s[8];
+            s[0] = fmaf(-2.f, __uint_as_float(r[8 * g + 0]), wa.x);
+            s[1] = fmaf(-2.f, __uint_as_float(r[8 * g + 1]), wa.y);
+            s[2] = fmaf(-2.f, __uint_as_float(r[8 * g + 2]), wa.z);
+            s[3] = fmaf(-2.f, __uint_as_float(r[8 * g + 3]), wa.w);
+            s[4] = fmaf(-2.f, __uint_as_float(r[8 * g + 4]), wb.x);
+            s[5] = fmaf(-2.f, __uint_as_float(r[8 * g + 5]), wb.y);
+            s[6] = fmaf(-2.f, __uint_as_float(r[8 * g + 6]), wb.z);
+            s[7] = fmaf(-2.f, __uint_as_float(r[8 * g + 7]), wb.w);
+            const float gm = fminf(fminf(fminf(s[0], s[1]), fminf(s[2], s[3])), fminf(fminf(s[4], s[5]), fminf(s[6], s[7])));
+            if (gm <= trk.thr) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                if (s[q] <= trk.thr) trk.push(s[q], col + 8 * g + q, my_idx, my_val);
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&bars->tmem_empty[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+      if (row < N) {
+        int out[kMaxCand];
+        int best;
+        const int cnt = trk.finish(my_idx, my_val, out, &best);
+        const int valid = cnt == DBGSOM_CAND_OVERFLOW ? 0 : cnt;
+#pragma unroll
+        for (int q = 0; q < kMaxCand; ++q) cand_idx[row * kMaxCand + q] = q < valid ? out[q] : -1;
+        cand_count[row] = (uint8_t)cnt;
+        idx_out[row * NB] = best;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// fp16 [rows, ld] row-major, box = 64 columns x box_rows, 128-byte swizzle, zero fill out of bounds
+int make_map(CUtensorMap* map, const uint16_t* base, int64_t rows, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return DBGSOM_E_DRIVER;
+  const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  const cuuint32_t elem[2] = {1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<uint16_t*>(base), dims, strides, box, elem,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? DBGSOM_OK : DBGSOM_E_DRIVER;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int NPASS, int NB, int BN, bool XRES>
+int launch_cfg(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t s) {
+  using C = Cfg<NPASS, BN, XRES>;
+  CUtensorMap mxh, mxl, mwh, mwl;
+  int rc = make_map(&mxh, a.d_X16_hi, a.N, a.ld16, BM);
+  if (rc) return rc;
+  rc = make_map(&mwh, a.d_W16_hi, a.Mpad, a.ld16, BN);
+  if (rc) return rc;
+  if (NPASS == 3) {
+    rc = make_map(&mxl, a.d_X16_lo, a.N, a.ld16, BM);
+    if (rc) return rc;
+    rc = make_map(&mwl, a.d_W16_lo, a.Mpad, a.ld16, BN);
+    if (rc) return rc;
+  } else {
+    mxl = mxh;
+    mwl = mwh;
+  }
+  auto kern = bmu_cand_tensor_kernel<NPASS, NB, BN, XRES>;
+  DBGSOM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  const int KB = (int)(a.ld16 / BK);
+  const int NT = ceil_div(a.M, BN);
+  int64_t grid = ceil_div<int64_t>(a.N, BM);
+  if (grid > sm_count()) grid = sm_count();
+  kern<<<(unsigned)grid, TC_THREADS, C::SMEM_BYTES, s>>>(mxh, mxl, mwh, mwl, a.N, KB, NT, a.d_wnorm, a.d_xnorm16,
+                                                        a.d_wmax, tensor_bound_coef(NPASS, a.bound_scale), a.d_idx,
+                                                        ws.cand_idx, ws.cand_count);
+  DBGSOM_LAUNCH_CHECK();
+  return DBGSOM_OK;
+}
+
+template <int NPASS, int NB>
+int launch_shape(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t s) {
+  const int KB = (int)(a.ld16 / BK);
+  constexpr int BN = NPASS == 1 ? 256 : 128;
+  if (KB <= MAX_RES_KB) return launch_cfg<NPASS, NB, BN, true>(a, ws, s);
+  return launch_cfg<NPASS, NB, BN, false>(a, ws, s);
+}
+
+}  // namespace
+
+int launch_bmu_cand_tensor(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t s) {
+  if (a.ld16 % BK != 0 || a.Mpad % 256 != 0 || a.Mpad < a.M) return DBGSOM_E_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(a.d_X16_hi) & 15u) || (reinterpret_cast<uintptr_t>(a.d_W16_hi) & 15u) ||
+      (reinterpret_cast<uintptr_t>(a.d_wnorm) & 15u))
+    return DBGSOM_E_UNSUPPORTED;
+  if (a.N > 0x7fffff00LL) return DBGSOM_E_UNSUPPORTED;  // TMA coordinates are int32
+  if (a.n_pass == 1) return a.n_bmu == 1 ? launch_shape<1, 1>(a, ws, s) : launch_shape<1, 2>(a, ws, s);
+  return a.n_bmu == 1 ? launch_shape<3, 1>(a, ws, s) : launch_shape<3, 2>(a, ws, s);
+}
+
+}  // namespace dbgsom

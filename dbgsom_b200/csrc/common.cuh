@@ -1,0 +1,194 @@
+// Shared helpers for the dbgsom_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/dbgsom_b200.h"
+
+#define DBGSOM_CUDA_TRY(expr)                  \
+  do {                                         \
+    cudaError_t _e = (expr);                   \
+    if (_e != cudaSuccess) return (int)_e;     \
+  } while (0)
+
+#define DBGSOM_LAUNCH_CHECK()                  \
+  do {                                         \
+    cudaError_t _e = cudaGetLastError();       \
+    if (_e != cudaSuccess) return (int)_e;     \
+  } while (0)
+
+namespace dbgsom {
+
+constexpr int kMaxCand = DBGSOM_MAX_CAND;
+constexpr unsigned kFullMask = 0xffffffffu;
+
+template <typename T>
+__host__ __device__ constexpr T ceil_div(T a, T b) {
+  return (a + b - 1) / b;
+}
+template <typename T>
+__host__ __device__ constexpr T round_up(T a, T b) {
+  return ceil_div(a, b) * b;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFullMask, v, o));
+  return v;
+}
+
+// streaming 128-bit load that does not pollute L1 (data is read exactly once)
+__device__ __forceinline__ float4 ld_stream_f4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Candidate tracking shared by both BMU front ends.
+//
+// One thread owns one sample row and visits the approximate scores s~_j of all prototypes in
+// ascending j.  With m = the NB-th smallest score seen so far, a prototype is a candidate when
+// s~_j <= accept(m), where accept() widens m by the error bound of the front end (both the
+// candidate's and the incumbent's score may be off by the bound).  Because accept(m) only
+// shrinks as m shrinks, testing against the running value keeps a superset of the final set;
+// stale entries are filtered at the end.  The kMaxCand smallest accepted entries live in a small
+// table in shared memory; `evicted` remembers the best score that did not fit, so an entry that
+// would still qualify at the end but was dropped is detected (-> overflow, the sample is
+// re-scored against all prototypes).
+//
+// Bound model: accept(m) = (sqrt(max(m,0)) * (1 + rel) + abs_d)^2   when sq_domain (scores are
+// squared distances with a relative error `rel` and a distance-domain slack abs_d), or
+// accept(m) = m + abs_s (scores with an absolute error bound abs_s / 2).
+// ---------------------------------------------------------------------------------------------
+struct CandBound {
+  float rel;    // sq_domain: relative slack on the distance
+  float abs_d;  // sq_domain: absolute slack on the distance
+  float abs_s;  // linear domain: absolute slack on the score
+};
+
+template <int NB, bool SQ_DOMAIN>
+struct RowTracker {
+  float m1, m2, thr, evicted;
+  uint32_t n_app;
+  CandBound b;
+
+  __device__ __forceinline__ void init(const CandBound& bound) {
+    m1 = 3.0e38f;
+    m2 = 3.0e38f;
+    thr = 3.0e38f;  // finite: padded prototypes carry +inf scores and are never accepted
+    evicted = __int_as_float(0x7f800000);
+    n_app = 0;
+    b = bound;
+  }
+  __device__ __forceinline__ float accept(float m) const {
+    if (m >= 1.0e38f) return 3.0e38f;
+    if (SQ_DOMAIN) {
+      float r = sqrtf(fmaxf(m, 0.f)) * (1.f + b.rel) + b.abs_d;
+      return r * r * (1.f + 4.8e-7f);
+    }
+    return m + b.abs_s;
+  }
+  // slow path: called only when s <= thr.  The ring keeps the kMaxCand smallest scores seen.
+  __device__ __forceinline__ void push(float s, int j, int* ring_idx, float* ring_val) {
+    if (n_app < (uint32_t)kMaxCand) {
+      ring_idx[n_app] = j;
+      ring_val[n_app] = s;
+    } else {
+      int worst = 0;
+      float wv = ring_val[0];
+#pragma unroll
+      for (int q = 1; q < kMaxCand; ++q) {
+        const float v = ring_val[q];
+        if (v > wv) {
+          wv = v;
+          worst = q;
+        }
+      }
+      if (s < wv) {
+        evicted = fminf(evicted, wv);
+        ring_idx[worst] = j;
+        ring_val[worst] = s;
+      } else {
+        evicted = fminf(evicted, s);
+      }
+    }
+    ++n_app;
+    if (s < m1) {
+      m2 = m1;
+      m1 = s;
+    } else if (s < m2) {
+      m2 = s;
+    }
+    thr = accept(NB == 1 ? m1 : m2);
+  }
+  // final: compact valid candidates to out_idx[0..count) ; returns count or DBGSOM_CAND_OVERFLOW
+  __device__ __forceinline__ int finish(const int* ring_idx, const float* ring_val, int* out_idx,
+                                        int* best_idx) const {
+    const int have = n_app < (uint32_t)kMaxCand ? (int)n_app : kMaxCand;
+    int cnt = 0, bi = -1;
+    float bv = __int_as_float(0x7f800000);
+    for (int q = 0; q < have; ++q) {
+      const float v = ring_val[q];
+      const int j = ring_idx[q];
+      if (v <= thr) {
+        out_idx[cnt++] = j;
+        if (v < bv || (v == bv && j < bi)) {
+          bv = v;
+          bi = j;
+        }
+      }
+    }
+    *best_idx = bi;
+    if (evicted <= thr) return DBGSOM_CAND_OVERFLOW;
+    return cnt;
+  }
+};
+
+// Absolute bound on |approximate - exact score| of the tensor front end for one sample, in the
+// scaled score units of the shadows (coef = bound_scale * 2^-9 for one pass, * 2^-19 for three:
+// input rounding, Cauchy-Schwarz), plus fp32 accumulation / bias rounding at the 2^-22 level.
+__device__ __forceinline__ float tensor_score_bound(float xnorm, const float* __restrict__ wmax, float coef) {
+  const float xw = xnorm * wmax[0];
+  return xw * coef + 2.4e-7f * (xw + wmax[2]);
+}
+__host__ __device__ inline float tensor_bound_coef(int n_pass, float bound_scale) {
+  const float k = bound_scale > 0.f ? bound_scale : 0.25f;
+  return k * (n_pass == 1 ? 1.953125e-3f : 1.9073486e-6f);
+}
+
+// workspace layout of the BMU search: [cand_idx int32 N*kMaxCand][cand_count uint8 N (padded)]
+struct BmuWorkspace {
+  int32_t* cand_idx;
+  uint8_t* cand_count;
+  __host__ static size_t bytes(int64_t N) {
+    return round_up<size_t>((size_t)N * kMaxCand * sizeof(int32_t), 256) + round_up<size_t>((size_t)N, 256);
+  }
+  __host__ static BmuWorkspace carve(void* base, int64_t N) {
+    BmuWorkspace w;
+    w.cand_idx = reinterpret_cast<int32_t*>(base);
+    w.cand_count = reinterpret_cast<uint8_t*>(base) + round_up<size_t>((size_t)N * kMaxCand * sizeof(int32_t), 256);
+    return w;
+  }
+};
+
+// internal launchers (defined in the .cu files, called from capi.cu)
+int launch_bmu_cand_simt(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t s);
+int launch_bmu_cand_tensor(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t s);
+int launch_bmu_resolve(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t s);
+
+}  // namespace dbgsom

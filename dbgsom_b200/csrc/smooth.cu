@@ -1,0 +1,214 @@
+// K3: neighbourhood smoothing  W <- (H . (n * C')) / (H . n)  in float64.
+//
+// Replaces (dbgsom/BaseSom.py): _calculate_gaussian_neighborhood :525-531 (H = exp(-hop^2/2sigma^2),
+// taken here from a host-computed table indexed by the integer hop count, bit-identical to the
+// reference's np.exp), Step 4 :509-515 (the reference materialises an M x M x D broadcast; this is
+// the same sum as a GEMM) and Step 5 :518-522 (sum_i ||W_i - W_new_i||).
+// Centres follow the reference's row packing (quirk Q1) when pack_rows != 0.
+#include "common.cuh"
+
+namespace dbgsom {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------ centres
+// single CTA: rank live neurons (n > 0), src[r] = index of the r-th live neuron (or -1)
+constexpr int RANK_THREADS = 1024;
+__global__ void __launch_bounds__(RANK_THREADS) live_rank_kernel(const double* __restrict__ n, int M, int pack,
+                                                                int32_t* __restrict__ src) {
+  __shared__ int32_t warp_tot[32];
+  __shared__ int32_t carry_sh;
+  if (threadIdx.x == 0) carry_sh = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < M; base += RANK_THREADS) {
+    const int j = base + threadIdx.x;
+    const int live = (j < M && n[j] > 0.0) ? 1 : 0;
+    if (j < M) src[j] = pack ? -1 : (live ? j : -1);
+    __syncthreads();  // all -1 defaults of this pass are written before any rank lands (rank <= j)
+    int v = live;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(kFullMask, v, o);
+      if (lane >= o) v += t;
+    }
+    if (lane == 31) warp_tot[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+      int t = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(kFullMask, t, o);
+        if (lane >= o) t += u;
+      }
+      warp_tot[lane] = t;
+    }
+    __syncthreads();
+    const int carry = carry_sh;
+    const int rank = carry + (warp ? warp_tot[warp - 1] : 0) + v - live;
+    if (pack && live) src[rank] = j;  // rank <= j: never clobbers a default written by a later pass
+    __syncthreads();
+    if (threadIdx.x == RANK_THREADS - 1) carry_sh = carry + warp_tot[31];
+    __syncthreads();
+  }
+}
+
+// B[j, :] = n_j * Sk[src_j, :] / sk[src_j]   (0 when src_j < 0);  den[i] = sum_j H_ij n_j
+__global__ void __launch_bounds__(256) weighted_centres_kernel(const double* __restrict__ part, int M, int D,
+                                                              const int32_t* __restrict__ src,
+                                                              double* __restrict__ B) {
+  const double* Sk = part;
+  const double* sk = part + (int64_t)M * D;
+  const double* n = sk + M;
+  const int64_t total = (int64_t)M * D;
+  for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (int64_t)gridDim.x * 256) {
+    const int j = (int)(e / D), d = (int)(e % D);
+    const int sj = src[j];
+    B[e] = sj >= 0 ? n[j] * (Sk[(int64_t)sj * D + d] / sk[sj]) : 0.0;
+  }
+}
+
+__global__ void __launch_bounds__(256) denominator_kernel(const uint16_t* __restrict__ hop, int64_t ldh,
+                                                         const double* __restrict__ lut, int lut_len,
+                                                         const double* __restrict__ n, int M,
+                                                         double* __restrict__ den) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= M) return;
+  double acc = 0.0;
+  for (int j = lane; j < M; j += 32) {
+    const unsigned h = hop[(int64_t)i * ldh + j];
+    if (h < (unsigned)lut_len) acc = fma(lut[h], n[j], acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) den[i] = acc;
+}
+
+// ------------------------------------------------------------------------------------------ GEMM
+// W_out[i, d] = (sum_j H_ij B[j, d]) / den[i];   tile 32 (i) x 64 (d), 32-wide j steps.
+constexpr int TI = 32, TD = 64, TJ = 32;
+__global__ void __launch_bounds__(256) smooth_gemm_kernel(const uint16_t* __restrict__ hop, int64_t ldh,
+                                                         const double* __restrict__ lut, int lut_len,
+                                                         const double* __restrict__ B, const double* __restrict__ den,
+                                                         int M, int D, double* __restrict__ W_out) {
+  __shared__ double Hs[TJ][TI + 2];
+  __shared__ double Bs[TJ][TD];
+  const int tid = threadIdx.x;
+  const int tx = tid % 16;  // 4 columns
+  const int ty = tid / 16;  // 2 rows
+  const int i0 = blockIdx.y * TI, d0 = blockIdx.x * TD;
+  double acc[2][4] = {};
+
+  for (int j0 = 0; j0 < M; j0 += TJ) {
+    // H tile: thread -> (i = tid / 8 ... , 4 consecutive j)
+    {
+      const int ii = tid / 8, jj = (tid % 8) * 4;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = i0 + ii, j = j0 + jj + q;
+        double h = 0.0;
+        if (i < M && j < M) {
+          const unsigned hp = hop[(int64_t)i * ldh + j];
+          if (hp < (unsigned)lut_len) h = lut[hp];
+        }
+        Hs[jj + q][ii] = h;
+      }
+    }
+    // B tile: 32 x 64 doubles, 8 per thread
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int e = tid + q * 256;
+      const int jj = e / TD, dd = e % TD;
+      const int j = j0 + jj, d = d0 + dd;
+      Bs[jj][dd] = (j < M && d < D) ? B[(int64_t)j * D + d] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int jj = 0; jj < TJ; ++jj) {
+      const double h0 = Hs[jj][ty * 2], h1 = Hs[jj][ty * 2 + 1];
+      const double2 b01 = *reinterpret_cast<const double2*>(&Bs[jj][tx * 4]);
+      const double2 b23 = *reinterpret_cast<const double2*>(&Bs[jj][tx * 4 + 2]);
+      acc[0][0] = fma(h0, b01.x, acc[0][0]); acc[0][1] = fma(h0, b01.y, acc[0][1]);
+      acc[0][2] = fma(h0, b23.x, acc[0][2]); acc[0][3] = fma(h0, b23.y, acc[0][3]);
+      acc[1][0] = fma(h1, b01.x, acc[1][0]); acc[1][1] = fma(h1, b01.y, acc[1][1]);
+      acc[1][2] = fma(h1, b23.x, acc[1][2]); acc[1][3] = fma(h1, b23.y, acc[1][3]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int i = i0 + ty * 2 + r;
+    if (i >= M) continue;
+    const double dn = den[i];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int d = d0 + tx * 4 + c;
+      if (d < D) W_out[(int64_t)i * D + d] = acc[r][c] / dn;
+    }
+  }
+}
+
+// change += ||W_in[i] - W_out[i]||_2, one warp per row
+__global__ void __launch_bounds__(256) change_kernel(const double* __restrict__ W_in, const double* __restrict__ W_out,
+                                                    int M, int D, double* __restrict__ change) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= M) return;
+  double acc = 0.0;
+  for (int d = lane; d < D; d += 32) {
+    const double t = W_in[(int64_t)i * D + d] - W_out[(int64_t)i * D + d];
+    acc = fma(t, t, acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) atomicAdd(change, sqrt(acc));
+}
+
+}  // namespace
+
+struct SmoothWorkspace {
+  int32_t* src;
+  double* den;
+  double* B;
+  static size_t bytes(int M, int D) {
+    return round_up<size_t>((size_t)M * 4, 256) + round_up<size_t>((size_t)M * 8, 256) + (size_t)M * D * 8;
+  }
+  static SmoothWorkspace carve(void* base, int M, int D) {
+    SmoothWorkspace w;
+    uint8_t* p = reinterpret_cast<uint8_t*>(base);
+    w.src = reinterpret_cast<int32_t*>(p);
+    p += round_up<size_t>((size_t)M * 4, 256);
+    w.den = reinterpret_cast<double*>(p);
+    p += round_up<size_t>((size_t)M * 8, 256);
+    w.B = reinterpret_cast<double*>(p);
+    return w;
+  }
+};
+
+size_t smooth_workspace_bytes(int M, int D) { return SmoothWorkspace::bytes(M, D); }
+
+int run_smooth(const dbgsom_smooth_args& a, cudaStream_t s) {
+  const SmoothWorkspace ws = SmoothWorkspace::carve(a.d_workspace, a.M, a.D);
+  const int M = a.M, D = a.D;
+  const double* n = a.d_part + (int64_t)M * D + M;
+  DBGSOM_CUDA_TRY(cudaMemsetAsync(a.d_change, 0, sizeof(double), s));
+  live_rank_kernel<<<1, RANK_THREADS, 0, s>>>(n, M, a.pack_rows, ws.src);
+  DBGSOM_LAUNCH_CHECK();
+  {
+    int64_t blocks = ceil_div<int64_t>((int64_t)M * D, 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    weighted_centres_kernel<<<(unsigned)blocks, 256, 0, s>>>(a.d_part, M, D, ws.src, ws.B);
+    DBGSOM_LAUNCH_CHECK();
+  }
+  denominator_kernel<<<ceil_div(M, 8), 256, 0, s>>>(a.d_hop, a.ldh, a.d_kernel_lut, a.lut_len, n, M, ws.den);
+  DBGSOM_LAUNCH_CHECK();
+  {
+    const dim3 grid(ceil_div(D, TD), ceil_div(M, TI));
+    smooth_gemm_kernel<<<grid, 256, 0, s>>>(a.d_hop, a.ldh, a.d_kernel_lut, a.lut_len, ws.B, ws.den, M, D, a.d_W_out);
+    DBGSOM_LAUNCH_CHECK();
+  }
+  change_kernel<<<ceil_div(M, 8), 256, 0, s>>>(a.d_W_in, a.d_W_out, M, D, a.d_change);
+  DBGSOM_LAUNCH_CHECK();
+  return DBGSOM_OK;
+}
+
+}  // namespace dbgsom

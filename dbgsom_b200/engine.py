@@ -1,0 +1,556 @@
+"""Device engine: owns the HBM buffers of one fit and drives the sm_100a kernels.
+
+PyTorch is used for device memory, streams and (when sharded) `torch.distributed`; every
+numeric step is a call into libdbgsom_b200.so through `_native` (include/dbgsom_b200.h).
+The engine mirrors the numeric seam of the reference's epoch body
+(`dbgsom/BaseSom.py:394-407`): BMU search -> sample weights + per-BMU sums -> neighbourhood
+smoothing, with the prototypes resident on the GPU for the whole fit.
+
+There is deliberately no CPU path here: constructing the engine without CUDA raises.
+"""
+
+from __future__ import annotations
+
+import math
+from typing import Sequence
+
+import numpy as np
+
+from . import _native as nat
+from .hostmath import class_entropy, column_moments_to_stats
+
+_UPLOAD_ROWS = 1 << 20
+
+
+def _round_up(a: int, b: int) -> int:
+    return (a + b - 1) // b * b
+
+
+class Comm:
+    """Thin wrapper over torch.distributed for the single collective of the path."""
+
+    def __init__(self, enabled: bool):
+        self.enabled = bool(enabled)
+        self.rank, self.world = 0, 1
+        if self.enabled:
+            import torch.distributed as dist
+
+            if not dist.is_available() or not dist.is_initialized():
+                raise RuntimeError("distributed=True needs an initialised torch.distributed process group")
+            self.dist = dist
+            self.rank, self.world = dist.get_rank(), dist.get_world_size()
+
+    def allreduce_(self, tensor, op: str = "sum"):
+        if self.enabled and self.world > 1:
+            ops = {"sum": self.dist.ReduceOp.SUM, "max": self.dist.ReduceOp.MAX, "min": self.dist.ReduceOp.MIN}
+            self.dist.all_reduce(tensor, op=ops[op])
+        return tensor
+
+    def broadcast_(self, tensor, src: int = 0):
+        if self.enabled and self.world > 1:
+            self.dist.broadcast(tensor, src=src)
+        return tensor
+
+    def exclusive_offset(self, n_local: int, device) -> tuple[int, int]:
+        """(offset of this rank's shard, global sample count)."""
+        if not (self.enabled and self.world > 1):
+            return 0, n_local
+        import torch
+
+        counts = torch.zeros(self.world, dtype=torch.int64, device=device)
+        counts[self.rank] = n_local
+        self.allreduce_(counts)
+        counts = counts.cpu().numpy()
+        return int(counts[: self.rank].sum()), int(counts.sum())
+
+
+class DeviceEngine:
+    """One fit's worth of device state.  See module docstring."""
+
+    def __init__(
+        self,
+        device: str = "cuda",
+        bmu_backend: str = "auto",
+        distributed: bool = False,
+        bound_scale: float = 0.0,
+        strict_ties: bool = False,
+    ) -> None:
+        import torch
+
+        self.torch = torch
+        self.lib = nat.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("dbgsom_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.dev = torch.device(device)
+        if self.dev.type != "cuda":
+            raise ValueError(f"device must be a CUDA device, got {device!r}")
+        if self.dev.index is None:
+            self.dev = torch.device("cuda", torch.cuda.current_device())
+        nat.check(self.lib.dbgsom_check_device(self.dev.index), "dbgsom_check_device")
+        if bmu_backend not in ("auto", "tensor", "tensor1", "simt"):
+            raise ValueError("bmu_backend must be 'auto', 'tensor', 'tensor1' or 'simt'")
+        self.bmu_backend = bmu_backend
+        self.bound_scale = float(bound_scale)
+        self.strict_ties = bool(strict_ties)
+        self.comm = Comm(distributed)
+        self.sample_offset = 0
+        self.n_samples_global = 0
+        self.launches = 0  # kernels + memsets enqueued by this engine (bench bookkeeping)
+        self._prof = None
+        self.last_bmu_stats = None
+        self._ws = {}
+        self.X = None
+        self.W = None
+        self.M = 0
+        self.n_previous_rows = 0
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return self.torch.cuda.current_stream(self.dev).cuda_stream
+
+    def enable_profiling(self, on: bool = True) -> None:
+        """Record CUDA-event pairs around every phase of `epoch` (read with `phase_times_ms`)."""
+        self._prof = {} if on else None
+
+    class _Phase:
+        def __init__(self, eng, name):
+            self.eng, self.name = eng, name
+
+        def __enter__(self):
+            if self.eng._prof is not None:
+                ev = self.eng.torch.cuda.Event
+                self.t0, self.t1 = ev(enable_timing=True), ev(enable_timing=True)
+                self.t0.record(self.eng.torch.cuda.current_stream(self.eng.dev))
+
+        def __exit__(self, *exc):
+            if self.eng._prof is not None:
+                self.t1.record(self.eng.torch.cuda.current_stream(self.eng.dev))
+                self.eng._prof.setdefault(self.name, []).append((self.t0, self.t1))
+
+    def phase_times_ms(self, reset: bool = True) -> dict:
+        """Mean device time per phase and call over the recorded epochs (synchronises)."""
+        self.torch.cuda.synchronize(self.dev)
+        out = {k: [a.elapsed_time(b) for a, b in v] for k, v in (self._prof or {}).items()}
+        if reset and self._prof is not None:
+            self._prof = {}
+        return out
+
+    def _workspace(self, key: str, nbytes: int):
+        buf = self._ws.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = self.torch.empty(max(int(nbytes), 256), dtype=self.torch.uint8, device=self.dev)
+            self._ws[key] = buf
+        return buf
+
+    def _upload_matrix(self, X: np.ndarray):
+        """Host [N, D] (float32/float64) -> device float32 [N, ldx], zero padded to ldx = 4k."""
+        torch = self.torch
+        n, d = X.shape
+        ldx = _round_up(d, 4)
+        out = torch.zeros((n, ldx), dtype=torch.float32, device=self.dev) if ldx != d else torch.empty(
+            (n, ldx), dtype=torch.float32, device=self.dev
+        )
+        for s in range(0, n, _UPLOAD_ROWS):
+            chunk = np.ascontiguousarray(X[s : s + _UPLOAD_ROWS])
+            out[s : s + chunk.shape[0], :d] = torch.from_numpy(chunk).to(self.dev, non_blocking=False).to(torch.float32)
+        return out
+
+    def close(self) -> None:
+        self._ws.clear()
+        for name in ("X", "X16_hi", "X16_lo", "xnorm16", "W", "W32", "W16_hi", "W16_lo", "labels", "part", "hop"):
+            if hasattr(self, name):
+                setattr(self, name, None)
+
+    # ------------------------------------------------------------------ data
+    def load_data(self, X: np.ndarray, y, n_classes: int) -> dict:
+        """Upload the samples and reduce the column statistics `fit` needs (K4)."""
+        torch = self.torch
+        with torch.cuda.device(self.dev):
+            self.N, self.D = int(X.shape[0]), int(X.shape[1])
+            self.X = self._upload_matrix(X)
+            self.ldx = int(self.X.shape[1])
+            self.n_classes = int(n_classes)
+            self.labels = None
+            if y is not None:
+                self.labels = torch.from_numpy(np.ascontiguousarray(y, dtype=np.int32)).to(self.dev)
+            self.sample_offset, self.n_samples_global = self.comm.exclusive_offset(self.N, self.dev)
+            return self._column_statistics()
+
+    def _column_statistics(self) -> dict:
+        torch = self.torch
+        # K4: moments about a common data row (rank 0's first row)
+        shift_row = self.X[0].clone()
+        self.comm.broadcast_(shift_row, 0)
+        moments = torch.zeros(2 * self.ldx + 1, dtype=torch.float64, device=self.dev)
+        nat.check(
+            self.lib.dbgsom_colstats(
+                self.X.data_ptr(), self.N, self.ldx, self.ldx, shift_row.data_ptr(), moments.data_ptr(), self._stream()
+            ),
+            "dbgsom_colstats",
+        )
+        self.launches += 1
+        self.comm.allreduce_(moments[: 2 * self.ldx])
+        self.comm.allreduce_(moments[2 * self.ldx :], "max")
+        m = moments.cpu().numpy()
+        s1, s2, maxabs = m[: self.ldx], m[self.ldx : 2 * self.ldx], float(m[2 * self.ldx])
+        stats = column_moments_to_stats(self.n_samples_global, s1, s2)
+        self.total_variance = stats["total_variance"]
+        # data mean (centres the fp16 shadow) and a power-of-two scale that keeps it in range
+        mean = shift_row.double().cpu().numpy() + s1 / self.n_samples_global
+        self.shift = torch.from_numpy(mean.astype(np.float32)).to(self.dev)
+        # |x'| <= 2^12 leaves a factor 16 of fp16 range for prototypes outside the data hull
+        self.scale = 1.0 if not (maxabs > 0 and math.isfinite(maxabs)) else 2.0 ** math.floor(
+            math.log2(2.0**12 / (2.0 * maxabs))
+        )
+        self.X16_hi = self.X16_lo = self.xnorm16 = None
+        self.ld16 = _round_up(self.ldx, 64)
+        return stats
+
+    def load_device_data(self, X_dev, labels_dev=None, n_classes: int = 0) -> dict:
+        """Like `load_data` for samples that already live in HBM (float32 [N, D], D % 4 == 0)."""
+        torch = self.torch
+        if X_dev.dtype != torch.float32 or X_dev.dim() != 2 or not X_dev.is_contiguous() or X_dev.shape[1] % 4:
+            raise ValueError("X_dev must be a contiguous float32 [N, D] CUDA tensor with D % 4 == 0")
+        with torch.cuda.device(self.dev):
+            self.N, self.D = int(X_dev.shape[0]), int(X_dev.shape[1])
+            self.X, self.ldx = X_dev, int(X_dev.shape[1])
+            self.n_classes, self.labels = int(n_classes), labels_dev
+            self.sample_offset, self.n_samples_global = self.comm.exclusive_offset(self.N, self.dev)
+            return self._column_statistics()
+
+    def _ensure_x16(self, need_lo: bool) -> None:
+        torch = self.torch
+        if self.X16_hi is not None and (self.X16_lo is not None or not need_lo):
+            return
+        self.X16_hi = torch.empty((self.N, self.ld16), dtype=torch.float16, device=self.dev)
+        self.X16_lo = torch.empty((self.N, self.ld16), dtype=torch.float16, device=self.dev) if need_lo else None
+        self.xnorm16 = torch.empty(self.N, dtype=torch.float32, device=self.dev)
+        nat.check(
+            self.lib.dbgsom_prepare_x16(
+                self.X.data_ptr(), self.N, self.ldx, self.ldx, self.shift.data_ptr(), self.scale,
+                self.X16_hi.data_ptr(), self.X16_lo.data_ptr() if need_lo else None, self.ld16,
+                self.xnorm16.data_ptr(), self._stream(),
+            ),
+            "dbgsom_prepare_x16",
+        )
+        self.launches += 1
+
+    # ------------------------------------------------------------------ map state
+    def _alloc_map(self, capacity: int) -> None:
+        torch = self.torch
+        cap = _round_up(max(int(capacity), 4), 256)
+        old = self.W
+        self.cap = cap
+        self.W = [torch.zeros((cap, self.ldx), dtype=torch.float64, device=self.dev) for _ in range(2)]
+        self.W32 = torch.zeros((cap, self.ldx), dtype=torch.float32, device=self.dev)
+        self.W16_hi = self.W16_lo = None
+        self.wnorm = torch.empty(cap, dtype=torch.float32, device=self.dev)
+        self.wshift = torch.empty(self.ldx, dtype=torch.float64, device=self.dev)
+        self.wmax = torch.zeros(4, dtype=torch.float32, device=self.dev)  # see dbgsom_prepare_w
+        self.part = torch.zeros(cap * self.ldx + 3 * cap, dtype=torch.float64, device=self.dev)
+        self.change = torch.zeros(1, dtype=torch.float64, device=self.dev)
+        self.idx = torch.empty((self.N, 2), dtype=torch.int32, device=self.dev)
+        self.bmu_stats = torch.zeros(4, dtype=torch.int64, device=self.dev)
+        self.class_hist = (
+            torch.zeros((cap, self.n_classes), dtype=torch.int32, device=self.dev) if self.labels is not None else None
+        )
+        if old is not None:
+            for new, prev in zip(self.W, old):
+                new[: prev.shape[0]] = prev
+
+    def _ensure_capacity(self, m: int) -> None:
+        if m > self.cap:
+            self._alloc_map(max(2 * self.cap, m))
+
+    def init_map_from_rows(self, rows: Sequence[int], capacity: int) -> None:
+        """Start prototypes = the given global sample rows (dbgsom/BaseSom.py:423-430)."""
+        torch = self.torch
+        with torch.cuda.device(self.dev):
+            self.W = None
+            self._alloc_map(capacity)
+            self.cur = 0
+            rows = np.asarray(rows, dtype=np.int64)
+            local = rows - self.sample_offset
+            owned = (local >= 0) & (local < self.N)
+            W0 = self.W[0]
+            if owned.any():
+                src = torch.from_numpy(np.where(owned, local, 0)).to(self.dev)
+                tmp = torch.zeros((len(rows), self.ldx), dtype=torch.float64, device=self.dev)
+                nat.check(
+                    self.lib.dbgsom_gather_rows(
+                        self.X.data_ptr(), self.ldx, self.ldx, src.data_ptr(), len(rows), tmp.data_ptr(), self._stream()
+                    ),
+                    "dbgsom_gather_rows",
+                )
+                self.launches += 1
+                tmp[torch.from_numpy(~owned).to(self.dev)] = 0
+                W0[: len(rows)] = tmp
+            else:
+                W0[: len(rows)] = 0
+            self.comm.allreduce_(W0[: len(rows)])
+            self.M = len(rows)
+            self.n_previous_rows = self.M
+
+    def set_map(self, W: np.ndarray) -> None:
+        """Replace the prototypes by a host matrix [M, D] (fixed-map training, tests)."""
+        torch = self.torch
+        with torch.cuda.device(self.dev):
+            m = int(W.shape[0])
+            if self.W is None:
+                self._alloc_map(m)
+                self.cur = 0
+            self._ensure_capacity(m)
+            cur = self.W[self.cur]
+            cur.zero_()
+            cur[:m, : self.D] = torch.from_numpy(np.ascontiguousarray(W, dtype=np.float64)).to(self.dev)
+            self.M = m
+            self.n_previous_rows = m
+
+    def set_hops(self, hop_u16: np.ndarray) -> None:
+        torch = self.torch
+        m = hop_u16.shape[0]
+        finite = hop_u16[hop_u16 != 0xFFFF]
+        self.hop_max = int(finite.max()) if finite.size else 0
+        # uint16 travels as int16 bit patterns (torch has no uint16 arithmetic; none is needed)
+        self.hop = torch.from_numpy(np.ascontiguousarray(hop_u16).view(np.int16)).to(self.dev)
+        self.ldh = m
+
+    def apply_row_ops(self, ops, n_rows: int) -> None:
+        """Prototype rows of the neurons a growth step inserted (see topology.RowOp)."""
+        torch = self.torch
+        with torch.cuda.device(self.dev):
+            self._ensure_capacity(n_rows)
+            flat = np.array([(o.dst, o.a, o.b, o.c) for o in ops], dtype=np.int32).reshape(-1, 4)
+            d_ops = torch.from_numpy(flat).to(self.dev)
+            nat.check(
+                self.lib.dbgsom_apply_row_ops(
+                    self.W[self.cur].data_ptr(), self.ldx, d_ops.data_ptr(), len(ops), self._stream()
+                ),
+                "dbgsom_apply_row_ops",
+            )
+            self.launches += 1
+            self.M = int(n_rows)
+
+    def keep_rows(self, alive: np.ndarray) -> None:
+        """Drop all prototype rows but `alive` (dead-neuron removal at the end of fit)."""
+        torch = self.torch
+        idx = torch.from_numpy(np.asarray(alive, dtype=np.int64)).to(self.dev)
+        cur = self.W[self.cur]
+        kept = cur.index_select(0, idx)
+        cur.zero_()
+        cur[: kept.shape[0]] = kept
+        self.M = int(kept.shape[0])
+
+    def weights(self) -> np.ndarray:
+        return self.W[self.cur][: self.M, : self.D].cpu().numpy()
+
+    # ------------------------------------------------------------------ kernels
+    def _pick_backend(self, n: int, m: int) -> tuple[int, int]:
+        """(backend, n_pass).  The tensor path pays off once the distance matrix is large."""
+        mode = self.bmu_backend
+        if mode == "simt":
+            return nat.BMU_SIMT, 0
+        if mode == "tensor":
+            return nat.BMU_TENSOR, 3
+        if mode == "tensor1":
+            return nat.BMU_TENSOR, 1
+        big = m >= 128 and n * m * self.ldx >= (1 << 31)
+        return (nat.BMU_TENSOR, 3) if big else (nat.BMU_SIMT, 0)
+
+    def _prepare_w(self, W, m: int, tensor: bool, need_lo: bool) -> int:
+        torch = self.torch
+        mpad = _round_up(m, 256)
+        if tensor:
+            if self.W16_hi is None or self.W16_hi.shape[0] < mpad or (need_lo and self.W16_lo is None):
+                rows = _round_up(max(mpad, self.cap), 256)
+                self.W16_hi = torch.zeros((rows, self.ld16), dtype=torch.float16, device=self.dev)
+                self.W16_lo = torch.zeros((rows, self.ld16), dtype=torch.float16, device=self.dev) if need_lo else None
+                self.wnorm = torch.empty(rows, dtype=torch.float32, device=self.dev)
+        nat.check(
+            self.lib.dbgsom_prepare_w(
+                W.data_ptr(), m, self.ldx, self.shift.data_ptr(), self.scale, self.W32.data_ptr(),
+                self.W16_hi.data_ptr() if tensor else None,
+                self.W16_lo.data_ptr() if (tensor and need_lo) else None,
+                self.ld16, mpad, self.wnorm.data_ptr() if tensor else None,
+                self.wshift.data_ptr() if tensor else None, self.wmax.data_ptr(), self._stream(),
+            ),
+            "dbgsom_prepare_w",
+        )
+        self.launches += 3 if tensor else 2
+        return mpad
+
+    def _run_bmu(self, X, n: int, ldx: int, x16, W, m: int, n_bmu: int, want_dist: bool, idx, dist, backend=None):
+        """prepare_w + candidate search + exact re-score for samples X against prototypes W."""
+        be, n_pass = self._pick_backend(n, m) if backend is None else backend
+        tensor = be == nat.BMU_TENSOR
+        if W.shape[0] > self.W32.shape[0]:
+            self.W32 = self.torch.zeros((W.shape[0], self.ldx), dtype=self.torch.float32, device=self.dev)
+        with self._Phase(self, "prepare_w"):
+            mpad = self._prepare_w(W, m, tensor, n_pass == 3)
+        ws_bytes = self.lib.dbgsom_bmu_workspace_bytes(n, n_bmu)
+        ws = self._workspace("bmu", ws_bytes)
+        self.bmu_stats.zero_()
+        a = nat.BmuArgs()
+        a.d_X, a.N, a.D, a.ldx, a.ld16 = X.data_ptr(), n, self.ldx, ldx, self.ld16
+        if tensor:
+            xh, xl, xn = x16
+            a.d_X16_hi, a.d_X16_lo, a.d_xnorm16 = xh.data_ptr(), (xl.data_ptr() if xl is not None else None), xn.data_ptr()
+            a.d_W16_hi = self.W16_hi.data_ptr()
+            a.d_W16_lo = self.W16_lo.data_ptr() if self.W16_lo is not None else None
+            a.d_wnorm = self.wnorm.data_ptr()
+        a.d_W, a.d_W32, a.d_wmax = W.data_ptr(), self.W32.data_ptr(), self.wmax.data_ptr()
+        a.scale, a.M, a.Mpad, a.n_bmu = self.scale, m, mpad, n_bmu
+        a.backend, a.n_pass, a.bound_scale, a.tie_rel = be, n_pass, self.bound_scale, 0.0
+        a.strict, a.want_dist = int(self.strict_ties), int(want_dist)
+        a.d_idx, a.d_dist = idx.data_ptr(), (dist.data_ptr() if dist is not None else None)
+        a.d_stats = self.bmu_stats.data_ptr()
+        a.d_workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        with self._Phase(self, "bmu_candidates"):
+            nat.check(self.lib.dbgsom_bmu_candidates(a, self._stream()), "dbgsom_bmu_candidates")
+        with self._Phase(self, "bmu_resolve"):
+            nat.check(self.lib.dbgsom_bmu_resolve(a, self._stream()), "dbgsom_bmu_resolve")
+        self.launches += 3  # stats memset + candidate kernel + re-score kernel
+        self.last_backend = (be, n_pass)
+
+    def epoch(self, sigma: float, pack_rows: bool, entropy_error: bool, _force_simt: bool = False) -> dict:
+        """One training epoch on the resident data; returns per-neuron error, counts, change."""
+        torch = self.torch
+        with torch.cuda.device(self.dev):
+            m, cur = self.M, self.W[self.cur]
+            be = (nat.BMU_SIMT, 0) if _force_simt else self._pick_backend(self.N, m)
+            x16 = None
+            if be[0] == nat.BMU_TENSOR:
+                self._ensure_x16(be[1] == 3)
+                x16 = (self.X16_hi, self.X16_lo, self.xnorm16)
+            idx = self.idx.view(-1)[: self.N]
+            self._run_bmu(self.X, self.N, self.ldx, x16, cur, m, 1, False, idx, None, backend=be)
+
+            # K2
+            part = self.part[: m * self.ldx + 3 * m]
+            use_hist = entropy_error and self.labels is not None
+            acc = nat.AccumulateArgs()
+            acc.d_X, acc.N, acc.D, acc.ldx = self.X.data_ptr(), self.N, self.ldx, self.ldx
+            acc.d_bmu, acc.d_W32, acc.M = idx.data_ptr(), self.W32.data_ptr(), m
+            acc.inv_total_variance = 1.0 / self.total_variance if self.total_variance > 0 else float("inf")
+            acc.d_part = part.data_ptr()
+            acc.d_labels = self.labels.data_ptr() if use_hist else None
+            acc.n_classes = self.n_classes if use_hist else 0
+            acc.d_class_hist = self.class_hist.data_ptr() if use_hist else None
+            ws = self._workspace("acc", self.lib.dbgsom_accumulate_workspace_bytes(self.N, m))
+            acc.d_workspace, acc.workspace_bytes = ws.data_ptr(), ws.numel()
+            with self._Phase(self, "accumulate"):
+                nat.check(self.lib.dbgsom_accumulate(acc, self._stream()), "dbgsom_accumulate")
+            self.launches += 6 + (1 if use_hist else 0)
+
+            # the one collective of the path: per-neuron partial sums (+ class histogram)
+            with self._Phase(self, "allreduce"):
+                self.comm.allreduce_(part)
+                if use_hist:
+                    self.comm.allreduce_(self.class_hist[:m])
+
+            # K3
+            lut = np.exp(-(np.arange(self.hop_max + 1, dtype=np.float64) ** 2 / (2 * sigma**2)))
+            d_lut = torch.from_numpy(lut).to(self.dev)
+            out = self.W[self.cur ^ 1]
+            sm = nat.SmoothArgs()
+            sm.d_part, sm.d_hop, sm.ldh = part.data_ptr(), self.hop.data_ptr(), self.ldh
+            sm.d_kernel_lut, sm.lut_len = d_lut.data_ptr(), int(lut.size)
+            sm.M, sm.D, sm.pack_rows = m, self.ldx, int(bool(pack_rows))
+            sm.d_W_in, sm.d_W_out, sm.d_change = cur.data_ptr(), out.data_ptr(), self.change.data_ptr()
+            ws2 = self._workspace("smooth", self.lib.dbgsom_smooth_workspace_bytes(m, self.ldx))
+            sm.d_workspace, sm.workspace_bytes = ws2.data_ptr(), ws2.numel()
+            with self._Phase(self, "smooth"):
+                nat.check(self.lib.dbgsom_smooth(sm, self._stream()), "dbgsom_smooth")
+            self.launches += 6
+            self.cur ^= 1
+            self.n_previous_rows = m
+
+            # one small D2H (syncs): [sk | n | E | change | wmax]
+            tail = torch.cat([part[m * self.ldx :], self.change, self.wmax.double()]).cpu().numpy()
+            counts, err, change = tail[m : 2 * m], tail[2 * m : 3 * m], float(tail[3 * m])
+            if be[0] == nat.BMU_TENSOR and not tail[3 * m + 4] < 65000.0:
+                # a prototype left the fp16 range of the shadow (far outside the data hull): its
+                # scores were clamped, so redo this epoch on the fp32 path from the same state
+                self.cur ^= 1
+                return self.epoch(sigma, pack_rows, entropy_error, _force_simt=True)
+            if use_hist:
+                err = class_entropy(self.class_hist[:m].cpu().numpy())
+            self.last_bmu_stats = None
+            return {"error": err, "counts": counts, "change": change}
+
+    def bmu_stats_host(self) -> dict:
+        s = self.bmu_stats.cpu().numpy()
+        return {"ambiguous": int(s[0]), "flagged": int(s[1]), "candidates": int(s[2]), "full_rescans": int(s[3])}
+
+    def bmu_train(self, n_bmu: int, previous: bool = False):
+        """BMUs of the training samples against the current (or pre-update) prototypes."""
+        torch = self.torch
+        with torch.cuda.device(self.dev):
+            W = self.W[self.cur ^ 1] if previous else self.W[self.cur]
+            m = self.n_previous_rows if previous else self.M
+            n_bmu = min(n_bmu, m)
+            be = self._pick_backend(self.N, m)
+            x16 = None
+            if be[0] == nat.BMU_TENSOR:
+                self._ensure_x16(be[1] == 3)
+                x16 = (self.X16_hi, self.X16_lo, self.xnorm16)
+            idx = torch.empty((self.N, n_bmu), dtype=torch.int32, device=self.dev)
+            dist = torch.empty((self.N, n_bmu), dtype=torch.float64, device=self.dev)
+            self._run_bmu(self.X, self.N, self.ldx, x16, W, m, n_bmu, True, idx, dist, backend=be)
+            return dist.cpu().numpy(), idx.cpu().numpy().astype(np.int64)
+
+    def bmu(self, X: np.ndarray, W: np.ndarray, n_bmu: int):
+        """Stand-alone BMU search (predict path): host samples against host prototypes."""
+        torch = self.torch
+        with torch.cuda.device(self.dev):
+            n, d = int(X.shape[0]), int(X.shape[1])
+            if d != W.shape[1]:
+                raise ValueError(f"X has {d} features, the map has {W.shape[1]}")
+            self.N, self.D = n, d
+            self.X = self._upload_matrix(np.asarray(X))
+            self.ldx = int(self.X.shape[1])
+            self.ld16 = _round_up(self.ldx, 64)
+            self.labels, self.n_classes = None, 0
+            self.W = None
+            self._alloc_map(W.shape[0])
+            self.cur = 0
+            self.set_map(np.asarray(W))
+            # shadows for the tensor path: centre on the prototypes' mean, scale from both operands
+            be = self._pick_backend(n, self.M)
+            x16 = None
+            if be[0] == nat.BMU_TENSOR:
+                centre = np.asarray(W, dtype=np.float64).mean(axis=0)
+                shift = np.zeros(self.ldx, dtype=np.float32)
+                shift[:d] = centre
+                self.shift = torch.from_numpy(shift).to(self.dev)
+                maxabs = float(max(np.abs(np.asarray(X) - centre).max(), np.abs(np.asarray(W) - centre).max()))
+                self.scale = 1.0 if not (maxabs > 0 and math.isfinite(maxabs)) else 2.0 ** math.floor(
+                    math.log2(2.0**14 / maxabs)
+                )  # both operands are in hand here, so the bound is exact
+                self.X16_hi = None
+                self._ensure_x16(be[1] == 3)
+                x16 = (self.X16_hi, self.X16_lo, self.xnorm16)
+            else:
+                self.shift = torch.zeros(self.ldx, dtype=torch.float32, device=self.dev)
+                self.scale = 1.0
+            n_bmu = min(n_bmu, self.M)
+            idx = torch.empty((n, n_bmu), dtype=torch.int32, device=self.dev)
+            dist = torch.empty((n, n_bmu), dtype=torch.float64, device=self.dev)
+            self._run_bmu(self.X, n, self.ldx, x16, self.W[0], self.M, n_bmu, True, idx, dist, backend=be)
+            return dist.cpu().numpy(), idx.cpu().numpy().astype(np.int64)
+
+    # ------------------------------------------------------------------ host-side reductions
+    def allreduce_scalars(self, vals):
+        if not (self.comm.enabled and self.comm.world > 1):
+            return list(vals)
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.dev)
+        return self.comm.allreduce_(t).cpu().tolist()
+
+    def allreduce_arrays(self, arrs, op: str = "sum"):
+        if not (self.comm.enabled and self.comm.world > 1):
+            return list(arrs)
+        out = []
+        for a in arrs:
+            t = self.torch.from_numpy(np.ascontiguousarray(a)).to(self.dev)
+            out.append(self.comm.allreduce_(t, op).cpu().numpy())
+        return out

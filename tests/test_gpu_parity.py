@@ -1,0 +1,280 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle and the reference fixtures.
+
+All tests need a B200 (`-m gpu`).  Tolerances follow BASELINE.json's north star:
+  * BMU indices bit-equal to the float64 oracle wherever the oracle's relative gap between best
+    and second-best squared distance is >= 1e-6;
+  * prototypes within 1e-5 relative (max|dW| / max|W|) per epoch; counts exact; E within 1e-5.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import _datasets
+from conftest import golden_files
+from oracle import som_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+STEP_FILES = golden_files("step")
+TRAJ_FILES = golden_files("traj")
+GAP = 1e-6
+
+
+def engine(**kw):
+    from dbgsom_b200.engine import DeviceEngine
+
+    return DeviceEngine(**kw)
+
+
+def hop_u16(hop):
+    out = np.full(hop.shape, 0xFFFF, dtype=np.uint16)
+    fin = np.isfinite(hop)
+    out[fin] = hop[fin].astype(np.uint16)
+    return out
+
+
+def load_step(path):
+    g = np.load(path, allow_pickle=False)
+    meta = json.loads(str(g["meta"]))
+    X, _ = _datasets.load(meta["data"])
+    X = np.ascontiguousarray(X.astype(meta["cast"]))
+    return g, meta, X
+
+
+def assert_bmu_parity(idx, X, W, ref_idx=None):
+    """idx [N] from the device; exact match required outside the oracle's near-tie set."""
+    gap = O.relative_gap(X, W)
+    if ref_idx is None:
+        _, ref_idx = O.bmu_expansion(X, W, 1)
+    strict = gap >= GAP
+    bad = np.flatnonzero((idx != ref_idx) & strict)
+    assert bad.size == 0, f"{bad.size} BMU mismatches outside near-ties, first rows {bad[:5]}"
+    # inside the near-tie set the device winner must still be (numerically) as close
+    loose = np.flatnonzero(idx != ref_idx)
+    if loose.size:
+        d_dev = np.linalg.norm(X[loose].astype(np.float64) - W[idx[loose]], axis=1)
+        d_ref = np.linalg.norm(X[loose].astype(np.float64) - W[ref_idx[loose]], axis=1)
+        np.testing.assert_allclose(d_dev, d_ref, rtol=2e-6)
+    return int(strict.sum()), int(loose.size)
+
+
+# ------------------------------------------------------------------------------------------ K4
+def test_column_statistics():
+    X = _datasets.gmm(30000, 100, 8, 3) * 3.0 + 50.0  # large mean: cancellation check
+    e = engine()
+    stats = e.load_data(X, None, 0)
+    X64 = X.astype(np.float64)
+    assert stats["n_samples"] == X.shape[0]
+    assert stats["total_variance"] == pytest.approx(np.var(X64, axis=0).sum(), rel=1e-12)
+    assert stats["std_norm"] == pytest.approx(np.linalg.norm(np.std(X64, axis=0, ddof=1)), rel=1e-12)
+    np.testing.assert_allclose(e.shift.cpu().numpy()[:100], X64.mean(axis=0), rtol=1e-6)
+    e.close()
+
+
+# ------------------------------------------------------------------------------------------ K1
+@pytest.mark.parametrize("path", STEP_FILES, ids=[os.path.basename(p)[5:-4] for p in STEP_FILES])
+@pytest.mark.parametrize("backend", ["simt", "tensor", "tensor1"])
+def test_bmu_matches_reference_fixture(path, backend):
+    g, meta, X = load_step(path)
+    W = g["W"]
+    e = engine(bmu_backend=backend)
+    dist, idx = e.bmu(X, W, 1)
+    assert idx.shape == (X.shape[0], 1) and idx.dtype == np.int64
+    assert_bmu_parity(idx[:, 0], X, W, g["winners"])
+    np.testing.assert_allclose(dist[:, 0], g["dist"], rtol=1e-6, atol=2e-7)
+    dist2, idx2 = e.bmu(X, W, 2)
+    gap = O.relative_gap(X, W)
+    ok = gap >= GAP
+    np.testing.assert_array_equal(idx2[ok, 0], g["winners2"][ok, 0])
+    np.testing.assert_allclose(dist2, g["dist2"], rtol=1e-6, atol=2e-7)
+    assert (dist2[:, 0] <= dist2[:, 1]).all()
+    e.close()
+
+
+@pytest.mark.parametrize("backend,n_pass_name", [("simt", "fp32"), ("tensor", "3 pass"), ("tensor1", "1 pass")])
+@pytest.mark.parametrize("shape", [(20000, 256, 1024), (9000, 128, 4096), (5000, 784, 400), (3000, 1000, 300)])
+def test_bmu_large_maps(backend, n_pass_name, shape):
+    """Random-row prototypes (benign) and a smooth sheet (many near-ties) at bench-like shapes."""
+    n, d, m = shape
+    X = _datasets.gmm(n, d, 32, 11)
+    rng = np.random.default_rng(5)
+    W_rows = X[rng.choice(n, m, replace=False)].astype(np.float64)
+    # smooth sheet: heavily smoothed prototypes as after a large-sigma epoch
+    side = int(np.sqrt(m))
+    H = O.neighborhood(O.hop_matrix_grid(side, side), 4.0)
+    W_sheet = (H @ W_rows[: side * side]) / H.sum(axis=1)[:, None]
+    e = engine(bmu_backend=backend)
+    for name, W in (("rows", W_rows), ("sheet", W_sheet)):
+        dist, idx = e.bmu(X, W, 1)
+        n_strict, n_loose = assert_bmu_parity(idx[:, 0], X, W)
+        assert n_strict > 0.5 * n, name
+        d_ref = np.sqrt(np.maximum(O.sqdist_exact(X[:500], W)[np.arange(500), idx[:500, 0]], 0))
+        np.testing.assert_allclose(dist[:500, 0], d_ref, rtol=1e-9, atol=1e-9)
+    e.close()
+
+
+def test_bmu_duplicate_prototypes_lowest_index_wins():
+    """Exact ties go to the lowest index, like sklearn's heap (sklearn/utils/_heap.pyx:46)."""
+    X = _datasets.gmm(4000, 64, 4, 2)
+    W = X[:40].astype(np.float64)
+    W = np.concatenate([W, W[:20], W[:10]])  # rows 40..59 duplicate 0..19, rows 60..69 duplicate 0..9
+    for backend in ("simt", "tensor", "tensor1"):
+        e = engine(bmu_backend=backend)
+        _, idx = e.bmu(X, W, 1)
+        assert idx.max() < 40, backend
+        _, ref = O.bmu_expansion(X, W[:40], 1)
+        gap = O.relative_gap(X, W[:40])
+        np.testing.assert_array_equal(idx[gap >= GAP, 0], ref[gap >= GAP])
+        e.close()
+
+
+def test_bmu_ragged_and_tiny_shapes():
+    rng = np.random.default_rng(0)
+    for n, d, m in [(4, 3, 4), (1, 5, 2), (129, 17, 5), (1000, 65, 257), (257, 2, 300)]:
+        X = rng.normal(size=(n, d)).astype(np.float32)
+        W = rng.normal(size=(m, d))
+        for backend in ("simt", "tensor"):
+            e = engine(bmu_backend=backend)
+            dist, idx = e.bmu(X, W, min(2, m))
+            _, ref = O.bmu_expansion(X, W, min(2, m))
+            gap = O.relative_gap(X, W)
+            np.testing.assert_array_equal(idx[gap >= GAP, 0], ref.reshape(n, -1)[gap >= GAP, 0])
+            e.close()
+
+
+# ------------------------------------------------------------------------------------------ one epoch
+def run_epoch(X, W, hop, sigma, pack, backend="auto", y=None, n_classes=0, entropy=False):
+    e = engine(bmu_backend=backend)
+    stats = e.load_data(X, y, n_classes)
+    e.set_map(W)
+    e.set_hops(hop_u16(hop))
+    r = e.epoch(sigma, pack, entropy)
+    W_new = e.weights()
+    e.close()
+    return stats, r, W_new
+
+
+@pytest.mark.parametrize("path", STEP_FILES, ids=[os.path.basename(p)[5:-4] for p in STEP_FILES])
+@pytest.mark.parametrize("backend", ["simt", "tensor"])
+def test_epoch_matches_reference_fixture(path, backend):
+    g, meta, X = load_step(path)
+    stats, r, W_new = run_epoch(X, g["W"], g["hop"], float(g["sigma"]), True, backend)
+    assert stats["total_variance"] == pytest.approx(float(g["total_var"]), rel=1e-6)
+    ref = O.epoch_step(X, g["W"], g["hop"], float(g["sigma"]), float(g["total_var"]), pack=True)
+    gap = O.relative_gap(X, g["W"])
+    if (gap >= GAP).all():
+        np.testing.assert_array_equal(r["counts"], ref["n"])
+    np.testing.assert_allclose(r["error"], g["E"], rtol=1e-5, atol=1e-6)
+    scale = np.abs(g["W_new"]).max()
+    assert np.abs(W_new - g["W_new"]).max() / scale < 1e-5
+    assert r["change"] == pytest.approx(ref["change"], rel=1e-5)
+
+
+def test_epoch_aligned_rows_mode():
+    g, meta, X = load_step([p for p in STEP_FILES if "gmm64_6x6_dead" in p][0])
+    _, r, W_new = run_epoch(X, g["W"], g["hop"], float(g["sigma"]), False)
+    ref = O.epoch_step(X, g["W"], g["hop"], float(g["sigma"]), float(g["total_var"]), pack=False)
+    assert np.abs(W_new - ref["W_new"]).max() / np.abs(ref["W_new"]).max() < 1e-5
+    packed = O.epoch_step(X, g["W"], g["hop"], float(g["sigma"]), float(g["total_var"]), pack=True)
+    assert np.abs(W_new - packed["W_new"]).max() / np.abs(packed["W_new"]).max() > 1e-2
+
+
+@pytest.mark.parametrize("shape", [(40000, 256, 32), (20000, 784, 20), (6000, 2048, 12), (3000, 4096, 8)])
+def test_epoch_wide_rows_and_large_maps(shape):
+    """Every accumulate kernel configuration (D up to 4096) and a map with dead neurons."""
+    n, d, side = shape
+    X = _datasets.gmm(n, d, 16, 21)
+    m = side * side
+    rng = np.random.default_rng(1)
+    W = X[rng.choice(n, m, replace=False)].astype(np.float64)
+    W[3] += 1e3
+    W[m // 2] -= 1e3
+    hop = O.hop_matrix_grid(side, side)
+    sigma = 0.2 * side
+    stats, r, W_new = run_epoch(X, W, hop, sigma, True)
+    ref = O.epoch_step(X.astype(np.float64), W, hop, sigma, stats["total_variance"], pack=True, bmu_fn=O.bmu_expansion)
+    gap = O.relative_gap(X, W)
+    if (gap >= GAP).all():
+        np.testing.assert_array_equal(r["counts"], ref["n"])
+        assert r["counts"][3] == 0
+        np.testing.assert_allclose(r["error"], ref["E"], rtol=1e-5, atol=1e-6)
+        assert np.abs(W_new - ref["W_new"]).max() / np.abs(ref["W_new"]).max() < 1e-5
+    assert r["counts"].sum() == n
+
+
+def test_epoch_entropy_error():
+    X, lab = _datasets.gmm(5000, 32, 6, 3, return_labels=True)
+    W = X[:25].astype(np.float64)
+    hop = O.hop_matrix_grid(5, 5)
+    _, r, _ = run_epoch(X, W, hop, 1.0, True, y=lab.astype(np.int64), n_classes=6, entropy=True)
+    _, win = O.bmu_expansion(X, W, 1)
+    import scipy.stats
+
+    ref = np.array([scipy.stats.entropy(np.bincount(lab[win == j]), base=2) for j in range(25)])
+    np.testing.assert_allclose(r["error"], ref, rtol=1e-12, atol=1e-12)
+
+
+def test_full_size_properties_10m_rows():
+    """Size-independent checks at a BASELINE-sized shard (10M x 256 would take the oracle hours):
+    counts sum to N, sum of per-neuron sk-weighted sums equals the direct column sum, repeatability."""
+    import torch
+
+    n, d, side = 2_000_000, 256, 64
+    g = torch.Generator(device="cuda").manual_seed(0)
+    centers = torch.randn(64, d, device="cuda", generator=g) * 2
+    lab = torch.randint(0, 64, (n,), device="cuda", generator=g)
+    Xd = centers[lab] + torch.randn(n, d, device="cuda", generator=g)
+    X = Xd.cpu().numpy()
+    del Xd
+    W = X[np.random.default_rng(0).choice(n, side * side, replace=False)].astype(np.float64)
+    e = engine(bmu_backend="tensor")
+    e.load_data(X, None, 0)
+    e.set_map(W)
+    e.set_hops(hop_u16(O.hop_matrix_grid(side, side)))
+    r1 = e.epoch(12.8, True, False)
+    part = e.part[: side * side * d + 3 * side * side].cpu().numpy()
+    m = side * side
+    Sk, sk, cnt, E = part[: m * d].reshape(m, d), part[m * d : m * d + m], r1["counts"], r1["error"]
+    assert cnt.sum() == n and (cnt >= 0).all()
+    # winners of a sub-sample against the oracle
+    sub = np.random.default_rng(1).choice(n, 3000, replace=False)
+    idx = e.idx.view(-1)[:n].cpu().numpy()[sub]
+    assert_bmu_parity(idx.astype(np.int64), X[sub], W)
+    # linearity: sum_j Sk_j = sum_i k_i x_i, checked through sum_j sk_j bounds and E >= 0
+    assert (sk[cnt > 0] > 0).all() and (sk <= cnt + 1e-9).all() and (E >= 0).all()
+    assert np.isfinite(Sk).all()
+    e.set_map(W)
+    r2 = e.epoch(12.8, True, False)
+    np.testing.assert_array_equal(r1["counts"], r2["counts"])
+    np.testing.assert_allclose(r1["error"], r2["error"], rtol=1e-6)
+    e.close()
+
+
+# ------------------------------------------------------------------------------------------ full fits
+@pytest.mark.parametrize("path", TRAJ_FILES, ids=[os.path.basename(p)[5:-4] for p in TRAJ_FILES])
+def test_fit_matches_reference_fixture(path):
+    from dbgsom_b200 import SomClassifier, SomVQ
+
+    g = np.load(path, allow_pickle=False)
+    meta = json.loads(str(g["meta"]))
+    X, y = _datasets.load(meta["data"])
+    X = np.ascontiguousarray(X.astype(meta["cast"]))
+    is_vq = meta["est"] == "vq"
+    est = (SomVQ if is_vq else SomClassifier)(**meta["params"])
+    est.fit(X) if is_vq else est.fit(X, y)
+    # growth decisions are discrete: the same map must come out
+    np.testing.assert_array_equal(np.array(est.neurons_), g["neurons"])
+    assert est.n_iter_ == int(g["n_iter_"])
+    assert est.growing_threshold_ == pytest.approx(float(g["growing_threshold"]), rel=1e-9)
+    scale = np.abs(g["weights"]).max()
+    assert np.abs(est.weights_ - g["weights"]).max() / scale < 1e-4
+    assert est.quantization_error_ == pytest.approx(float(g["quantization_error"]), rel=1e-5)
+    assert est.topographic_error_ == pytest.approx(float(g["topographic_error"]), abs=2.0 / X.shape[0])
+    if is_vq:
+        assert np.mean(est.labels_ == g["labels"]) > 0.999
+        assert np.mean(est.predict(X[:200]) == g["predict_head"]) > 0.99
+    else:
+        np.testing.assert_array_equal(est.classes_, g["classes"])
+        assert est.score(X, y) == pytest.approx(float(g["score"]), abs=2e-3)

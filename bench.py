@@ -230,6 +230,7 @@ def run_ours(args, wl):
     # ------------------------------------------------------------------ timed region (device resident)
     sampler = ClockSampler(local)
     eng.enable_profiling(True)
+    eng.bmu_stats_host(reset=True)
     launches0 = eng.launches
     barrier()
     sampler.start()
@@ -339,7 +340,7 @@ def run_ours(args, wl):
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "roofline": roof, "roofline_update": roof_upd, "cpu_baseline": cpu,
             "phases_ms": {k_: mean(v) for k_, v in phases.items()},
-            "bmu_last_epoch": bmu_stats, "last_change": out["change"],
+            "bmu_rescore_per_epoch": {k_: v / args.steps for k_, v in bmu_stats.items()}, "last_change": out["change"],
         }
         print(json.dumps(line))
     eng.close()

@@ -64,7 +64,7 @@ class AccumulateArgs(C.Structure):
         ("D", c_int32),
         ("ldx", c_int64),
         ("d_bmu", c_void_p),
-        ("d_W32", c_void_p),
+        ("d_W", c_void_p),
         ("M", c_int32),
         ("inv_total_variance", c_double),
         ("d_part", c_void_p),

@@ -1,7 +1,7 @@
 // K2: sample weights + per-BMU segmented accumulation (HBM-bound; reads X exactly once).
 //
 // Replaces, per epoch (dbgsom/BaseSom.py):
-//   _calculate_exp_similarity                      :533-538   k_i = 1 - sqrt(1 - exp(-d_i^2 / V))
+//   _calculate_exp_similarity                      :533-538   k_i = 1 - sqrt(1 - exp(-d_i^2 / V))  (float64)
 //   np.argsort(winners) / np.unique(return_index)  :488-489   -> counting sort by winner
 //   numba_voronoi_set_centers                      :1028-1055 -> Sk_j = sum k_i x_i, sk_j = sum k_i
 //   neuron_activations                             :500-503   -> n_j
@@ -11,9 +11,14 @@
 //   histogram (counts per winner [+ class histogram]) -> exclusive scan (segment offsets, n_j as
 //   float64) -> scatter (sample permutation grouped by winner) -> segmented accumulate.
 // The accumulate kernel walks the permutation in fixed-size chunks; a team of warps owns a
-// chunk, keeps the current segment's prototype in registers (so the exact fp32 distance
-// ||x_i - w_b|| costs no extra memory traffic), accumulates k_i x_i in registers and flushes
-// with float64 atomics whenever the segment changes.  The M x D table is never privatised in
+// chunk, keeps the current segment's float64 prototype in registers (so the exact distance
+// ||x_i - w_b|| costs no extra memory traffic), accumulates k_i x_i in float64 registers and
+// flushes with float64 atomics whenever the segment changes.  Everything after the fp32 load
+// of x is float64, so the result is independent of the (atomic-ordered) permutation up to
+// 1e-16 and matches the reference to ~1e-13; its convergence test (sum ||dW|| < 1e-5,
+// dbgsom/BaseSom.py:519-522) needs that: with fp32 weights or partial sums the prototypes jitter
+// by ~1e-7 relative from epoch to epoch and the fit stops at a different epoch (or never).
+// B200 has the float64 rate for this (~3 DFMA per sample element, far below the HBM time).  The M x D table is never privatised in
 // shared memory (4 MB at 4096 x 256); traffic is N*(4D+8) + a few M*D words.
 #include "common.cuh"
 
@@ -130,28 +135,22 @@ __global__ void __launch_bounds__(SCAT_THREADS) scatter_kernel(const int32_t* __
 }
 
 // ------------------------------------------------------------------------------------------ accumulate
-// k = 1 - sqrt(1 - exp(-z)), z = d^2 / V >= 0, evaluated without cancellation at either end:
-// t = 1 - exp(-z) comes from expm1 (small z: samples sitting on a prototype) and
-// k = exp(-z) / (1 + sqrt(t)) is the conjugate form (large z: far outliers, k -> 0), so k keeps
-// fp32 relative accuracy over the whole range.
-__device__ __forceinline__ float sample_weight(float d2, float inv_var) {
-  const float z = d2 * inv_var;
-  const float t = -expm1f(-z);
-  return expf(-z) / (1.f + sqrtf(t));
-}
-
 constexpr int ACC_THREADS = 256;
 constexpr int ACC_CHUNK = 128;  // sorted positions per team task
 
-// VPL : float4 per lane per row slab;  WPR : warps cooperating on one row (team size).
+// VPL : float4 per lane per row slab;  WPR : warps cooperating on one row (team size);
+// U   : rows in flight per team (their loads are issued together and their sample weights are
+//       evaluated in one go, lane u doing row u, so the float64 exp/sqrt costs 1/U per row).
 // A team handles columns [tw * 128 * VPL, (tw + 1) * 128 * VPL) of each row with warp tw.
-template <int VPL, int WPR>
+// All arithmetic is float64: distances by direct differences, k = 1 - sqrt(1 - exp(-d^2 / V))
+// literally as dbgsom/BaseSom.py:536-537, sums in float64 registers.
+template <int VPL, int WPR, int U>
 __global__ void __launch_bounds__(ACC_THREADS) accumulate_kernel(
     const float* __restrict__ X, int64_t N, int D, int64_t ldx, const int32_t* __restrict__ perm,
-    const int32_t* __restrict__ offsets, const float* __restrict__ W32, int M, float inv_var,
+    const int32_t* __restrict__ offsets, const double* __restrict__ W, int M, double inv_var,
     double* __restrict__ part) {
   constexpr int TEAMS = ACC_THREADS / 32 / WPR;
-  __shared__ float red[TEAMS][2][WPR];  // cross-warp partial squared distances (double buffered)
+  __shared__ double red[TEAMS][2][WPR][U];  // cross-warp partial squared distances (double buffered)
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -165,6 +164,7 @@ __global__ void __launch_bounds__(ACC_THREADS) accumulate_kernel(
   double* __restrict__ En = sk + 2 * (int64_t)M;
 
   const int64_t n_tasks = ceil_div<int64_t>(total, ACC_CHUNK);
+  int parity = 0;
   for (int64_t task = (int64_t)blockIdx.x * TEAMS + team; task < n_tasks; task += (int64_t)gridDim.x * TEAMS) {
     const int32_t p0 = (int32_t)(task * ACC_CHUNK);
     const int32_t p1 = p0 + ACC_CHUNK < total ? p0 + ACC_CHUNK : total;
@@ -177,17 +177,23 @@ __global__ void __launch_bounds__(ACC_THREADS) accumulate_kernel(
     int seg = lo;
     int32_t seg_end = offsets[seg + 1];
 
-    float4 w[VPL], acc[VPL];
-    float run_k = 0.f, run_d = 0.f;
+    double w[VPL][4], acc[VPL][4];
+    double run_k = 0.0, run_d = 0.0;
     auto load_w = [&]() {
 #pragma unroll
       for (int v = 0; v < VPL; ++v) {
         const int c = col0 + v * 128;
-        w[v] = c < D ? *reinterpret_cast<const float4*>(W32 + (int64_t)seg * D + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < D) {
+          const double2 a = *reinterpret_cast<const double2*>(W + (int64_t)seg * D + c);
+          const double2 b = *reinterpret_cast<const double2*>(W + (int64_t)seg * D + c + 2);
+          w[v][0] = a.x; w[v][1] = a.y; w[v][2] = b.x; w[v][3] = b.y;
+        } else {
+          w[v][0] = w[v][1] = w[v][2] = w[v][3] = 0.0;
+        }
+        acc[v][0] = acc[v][1] = acc[v][2] = acc[v][3] = 0.0;
       }
-      run_k = 0.f;
-      run_d = 0.f;
+      run_k = 0.0;
+      run_d = 0.0;
     };
     auto flush = [&]() {
 #pragma unroll
@@ -195,92 +201,114 @@ __global__ void __launch_bounds__(ACC_THREADS) accumulate_kernel(
         const int c = col0 + v * 128;
         if (c < D) {
           double* dst = Sk + (int64_t)seg * D + c;
-          atomicAdd(dst + 0, (double)acc[v].x);
-          atomicAdd(dst + 1, (double)acc[v].y);
-          atomicAdd(dst + 2, (double)acc[v].z);
-          atomicAdd(dst + 3, (double)acc[v].w);
+          atomicAdd(dst + 0, acc[v][0]);
+          atomicAdd(dst + 1, acc[v][1]);
+          atomicAdd(dst + 2, acc[v][2]);
+          atomicAdd(dst + 3, acc[v][3]);
         }
       }
       if (tw == 0 && lane == 0) {
-        atomicAdd(sk + seg, (double)run_k);
-        atomicAdd(En + seg, (double)run_d);
+        atomicAdd(sk + seg, run_k);
+        atomicAdd(En + seg, run_d);
       }
     };
     load_w();
 
-    int parity = 0;
-    for (int32_t p = p0; p < p1; p += 2) {
-      // two rows in flight per iteration
-      const bool has2 = p + 1 < p1;
-      const int32_t r0 = perm[p];
-      const int32_t r1 = has2 ? perm[p + 1] : r0;
-      float4 x0[VPL], x1[VPL];
-#pragma unroll
-      for (int v = 0; v < VPL; ++v) {
-        const int c = col0 + v * 128;
-        x0[v] = c < D ? ld_stream_f4(X + (int64_t)r0 * ldx + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    int32_t p = p0;
+    while (p < p1) {
+      if (p >= seg_end) {  // entering a new segment (skipping empty ones)
+        flush();
+        do {
+          ++seg;
+          seg_end = offsets[seg + 1];
+        } while (p >= seg_end);
+        load_w();
       }
+      const int32_t lim = p1 < seg_end ? p1 : seg_end;
+      const int nb = lim - p < U ? lim - p : U;  // rows of this batch, all in the current segment
+
+      float4 x[U][VPL];
 #pragma unroll
-      for (int v = 0; v < VPL; ++v) {
-        const int c = col0 + v * 128;
-        x1[v] = (has2 && c < D) ? ld_stream_f4(X + (int64_t)r1 * ldx + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      for (int u = 0; u < U; ++u) {
+        if (u < nb) {
+          const int64_t r = perm[p + u];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        if (u == 1 && !has2) break;
-        const int32_t pp = p + u;
-        float4* x = u == 0 ? x0 : x1;
-        if (pp >= seg_end) {  // entering a new segment (skipping empty ones)
-          flush();
-          do {
-            ++seg;
-            seg_end = offsets[seg + 1];
-          } while (pp >= seg_end);
-          load_w();
-        }
-        float d2 = 0.f;
-#pragma unroll
-        for (int v = 0; v < VPL; ++v) {
-          const float a = x[v].x - w[v].x, b = x[v].y - w[v].y, c = x[v].z - w[v].z, e = x[v].w - w[v].w;
-          d2 = fmaf(a, a, d2);
-          d2 = fmaf(b, b, d2);
-          d2 = fmaf(c, c, d2);
-          d2 = fmaf(e, e, d2);
-        }
-        d2 = warp_sum(d2);
-        if (WPR > 1) {
-          if (lane == 0) red[team][parity][tw] = d2;
-          asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(WPR * 32));
-          d2 = 0.f;
-#pragma unroll
-          for (int q = 0; q < WPR; ++q) d2 += red[team][parity][q];
-          parity ^= 1;
-        }
-        const float k = sample_weight(d2, inv_var);
-        run_k += k;
-        run_d += sqrtf(d2);
-#pragma unroll
-        for (int v = 0; v < VPL; ++v) {
-          acc[v].x = fmaf(k, x[v].x, acc[v].x);
-          acc[v].y = fmaf(k, x[v].y, acc[v].y);
-          acc[v].z = fmaf(k, x[v].z, acc[v].z);
-          acc[v].w = fmaf(k, x[v].w, acc[v].w);
+          for (int v = 0; v < VPL; ++v) {
+            const int c = col0 + v * 128;
+            x[u][v] = c < D ? ld_stream_f4(X + r * ldx + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
       }
+      double d2[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        double t = 0.0;
+        if (u < nb) {
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) {
+            const double a = (double)x[u][v].x - w[v][0], b = (double)x[u][v].y - w[v][1];
+            const double c = (double)x[u][v].z - w[v][2], e = (double)x[u][v].w - w[v][3];
+            t = fma(a, a, t);
+            t = fma(b, b, t);
+            t = fma(c, c, t);
+            t = fma(e, e, t);
+          }
+          t = warp_sum(t);
+        }
+        d2[u] = t;
+      }
+      if (WPR > 1) {
+        if (lane == 0) {
+#pragma unroll
+          for (int u = 0; u < U; ++u) red[team][parity][tw][u] = d2[u];
+        }
+        asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(WPR * 32));
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          double t = 0.0;
+#pragma unroll
+          for (int q = 0; q < WPR; ++q) t += red[team][parity][q][u];
+          d2[u] = t;
+        }
+        parity ^= 1;
+      }
+      // lane u evaluates the weight and the distance of row u
+      double my_d2 = d2[0];
+#pragma unroll
+      for (int u = 1; u < U; ++u)
+        if ((lane % U) == u) my_d2 = d2[u];
+      const double my_dist = sqrt(my_d2);
+      const double my_k = 1.0 - sqrt(1.0 - exp(-inv_var * (my_dist * my_dist)));
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (u < nb) {
+          const double k = __shfl_sync(kFullMask, my_k, u);
+          run_k += k;
+          run_d += __shfl_sync(kFullMask, my_dist, u);
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) {
+            acc[v][0] = fma(k, (double)x[u][v].x, acc[v][0]);
+            acc[v][1] = fma(k, (double)x[u][v].y, acc[v][1]);
+            acc[v][2] = fma(k, (double)x[u][v].z, acc[v][2]);
+            acc[v][3] = fma(k, (double)x[u][v].w, acc[v][3]);
+          }
+        }
+      }
+      p += nb;
     }
     flush();
   }
 }
 
-template <int VPL, int WPR>
+template <int VPL, int WPR, int U>
 int launch_accumulate(const dbgsom_accumulate_args& a, const int32_t* perm, const int32_t* offsets, cudaStream_t s) {
   constexpr int TEAMS = ACC_THREADS / 32 / WPR;
   int64_t blocks = ceil_div<int64_t>(ceil_div<int64_t>(a.N, ACC_CHUNK), TEAMS);
   const int64_t cap = 148 * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  accumulate_kernel<VPL, WPR><<<(unsigned)blocks, ACC_THREADS, 0, s>>>(
-      a.d_X, a.N, a.D, a.ldx, perm, offsets, a.d_W32, a.M, (float)a.inv_total_variance, a.d_part);
+  accumulate_kernel<VPL, WPR, U><<<(unsigned)blocks, ACC_THREADS, 0, s>>>(
+      a.d_X, a.N, a.D, a.ldx, perm, offsets, a.d_W, a.M, a.inv_total_variance, a.d_part);
   DBGSOM_LAUNCH_CHECK();
   return DBGSOM_OK;
 }
@@ -337,12 +365,12 @@ int run_accumulate(const dbgsom_accumulate_args& a, cudaStream_t s) {
     DBGSOM_LAUNCH_CHECK();
   }
   const int D4 = a.D;
-  if (D4 <= 128) return launch_accumulate<1, 1>(a, ws.perm, ws.offsets, s);
-  if (D4 <= 256) return launch_accumulate<2, 1>(a, ws.perm, ws.offsets, s);
-  if (D4 <= 512) return launch_accumulate<4, 1>(a, ws.perm, ws.offsets, s);
-  if (D4 <= 1024) return launch_accumulate<4, 2>(a, ws.perm, ws.offsets, s);
-  if (D4 <= 2048) return launch_accumulate<4, 4>(a, ws.perm, ws.offsets, s);
-  if (D4 <= 4096) return launch_accumulate<4, 8>(a, ws.perm, ws.offsets, s);
+  if (D4 <= 128) return launch_accumulate<1, 1, 4>(a, ws.perm, ws.offsets, s);
+  if (D4 <= 256) return launch_accumulate<2, 1, 4>(a, ws.perm, ws.offsets, s);
+  if (D4 <= 512) return launch_accumulate<4, 1, 2>(a, ws.perm, ws.offsets, s);
+  if (D4 <= 1024) return launch_accumulate<4, 2, 2>(a, ws.perm, ws.offsets, s);
+  if (D4 <= 2048) return launch_accumulate<4, 4, 2>(a, ws.perm, ws.offsets, s);
+  if (D4 <= 4096) return launch_accumulate<4, 8, 2>(a, ws.perm, ws.offsets, s);
   return DBGSOM_E_UNSUPPORTED;
 }
 

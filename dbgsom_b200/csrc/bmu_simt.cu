@@ -96,9 +96,18 @@ __global__ void __launch_bounds__(THREADS) bmu_cand_simt_kernel(const float* __r
       }
     __syncthreads();
     if (tid < BM) {
+      float a1 = __int_as_float(0x7f800000), a2 = a1;
       for (int c = 0; c < BN; ++c) {
         const float s = S[tid][c];
-        if (s <= trk.thr) trk.push(s, col0 + c, ring_idx[tid], ring_val[tid]);
+        if (NB == 2) a2 = fminf(a2, fmaxf(a1, s));
+        a1 = fminf(a1, s);
+      }
+      trk.observe(a1, a2);
+      if (a1 <= trk.thr) {
+        for (int c = 0; c < BN; ++c) {
+          const float s = S[tid][c];
+          if (s <= trk.thr) trk.offer(s, col0 + c, ring_idx[tid], ring_val[tid]);
+        }
       }
     }
     __syncthreads();

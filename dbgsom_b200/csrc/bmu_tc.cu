@@ -134,7 +134,7 @@ struct Cfg {
   static constexpr int B_TILE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = NA * B_TILE_BYTES + (XRES ? 0 : NA * A_TILE_BYTES);
   static constexpr int RES_BYTES = XRES ? MAX_RES_KB * NA * A_TILE_BYTES : 0;
-  static constexpr int RING_BYTES = BM * kMaxCand * 8;
+  static constexpr int RING_BYTES = BM * kMaxCand * 8 + BM * (BN / 32) * 4;  // candidate tables + chunk minima
   static constexpr int MISC_BYTES = 1024;  // barriers + tmem pointer
   static constexpr int SMEM_BUDGET = 227 * 1024 - 1024;  // minus alignment slack
   static constexpr int STAGES_RAW = (SMEM_BUDGET - RES_BYTES - RING_BYTES - MISC_BYTES) / STAGE_BYTES;
@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   Barriers* bars = reinterpret_cast<Barriers*>(ring + C::RING_BYTES);
   int* ring_idx = reinterpret_cast<int*>(ring);
   float* ring_val = reinterpret_cast<float*>(ring + BM * kMaxCand * 4);
+  float* chunk_min = reinterpret_cast<float*>(ring + BM * kMaxCand * 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -293,6 +294,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     int* my_idx = ring_idx + t * kMaxCand;
     float* my_val = ring_val + t * kMaxCand;
+    float* my_cmin = chunk_min + t;  // [chunk][row] -> conflict-free
     uint32_t acc = 0, acc_phase = 0;
     for (int64_t rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x) {
       const int64_t row = rt * BM + t;
@@ -308,30 +310,55 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         mbar_wait(&bars->tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t tmem_acc = tmem_base + lane_base + acc * BN;
+        // pass A: smallest score(s) of the tile, per 32-column chunk (kept for pass B)
+        float a1 = __int_as_float(0x7f800000), a2 = a1;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c = 0; c < BN / 32; ++c) {
           uint32_t r[32];
-          tmem_ld_32x32(tmem_acc + c0, r);
+          tmem_ld_32x32(tmem_acc + c * 32, r);
           tmem_ld_wait();
-          const int col = nt * BN + c0;
-          const float4* wn4 = reinterpret_cast<const float4*>(wnorm + col);
+          const float4* wn4 = reinterpret_cast<const float4*>(wnorm + nt * BN + c * 32);
+          float cm = __int_as_float(0x7f800000);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const float4 wa = __ldg(wn4 + 2 * g), wb = __ldg(wn4 + 2 * g + 1);
-            float s[8];
-            s[0] = fmaf(-2.f, __uint_as_float(r[8 * g + 0]), wa.x);
-            s[1] = fmaf(-2.f, __uint_as_float(r[8 * g + 1]), wa.y);
-            s[2] = fmaf(-2.f, __uint_as_float(r[8 * g + 2]), wa.z);
-            s[3] = fmaf(-2.f, __uint_as_float(r[8 * g + 3]), wa.w);
-            s[4] = fmaf(-2.f, __uint_as_float(r[8 * g + 4]), wb.x);
-            s[5] = fmaf(-2.f, __uint_as_float(r[8 * g + 5]), wb.y);
-            s[6] = fmaf(-2.f, __uint_as_float(r[8 * g + 6]), wb.z);
-            s[7] = fmaf(-2.f, __uint_as_float(r[8 * g + 7]), wb.w);
-            const float gm = fminf(fminf(fminf(s[0], s[1]), fminf(s[2], s[3])), fminf(fminf(s[4], s[5]), fminf(s[6], s[7])));
-            if (gm <= trk.thr) {
+          for (int g = 0; g < 8; ++g) {
+            const float4 w4 = __ldg(wn4 + g);
+            const float s0 = fmaf(-2.f, __uint_as_float(r[4 * g + 0]), w4.x);
+            const float s1 = fmaf(-2.f, __uint_as_float(r[4 * g + 1]), w4.y);
+            const float s2 = fmaf(-2.f, __uint_as_float(r[4 * g + 2]), w4.z);
+            const float s3 = fmaf(-2.f, __uint_as_float(r[4 * g + 3]), w4.w);
+            if (NB == 2) {
+              a2 = fminf(a2, fmaxf(a1, s0)); a1 = fminf(a1, s0);
+              a2 = fminf(a2, fmaxf(a1, s1)); a1 = fminf(a1, s1);
+              a2 = fminf(a2, fmaxf(a1, s2)); a1 = fminf(a1, s2);
+              a2 = fminf(a2, fmaxf(a1, s3)); a1 = fminf(a1, s3);
+            }
+            cm = fminf(fminf(cm, fminf(s0, s1)), fminf(s2, s3));
+          }
+          my_cmin[c * BM] = cm;
+          if (NB == 1) a1 = fminf(a1, cm);
+        }
+        trk.observe(a1, a2);
+        // pass B: only chunks in which some row of this warp may hold a candidate
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          const bool mine = my_cmin[c * BM] <= trk.thr;
+          if (!__any_sync(kFullMask, mine)) continue;
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_acc + c * 32, r);
+          tmem_ld_wait();
+          if (mine) {
+            const int col = nt * BN + c * 32;
+            const float4* wn4 = reinterpret_cast<const float4*>(wnorm + col);
 #pragma unroll
-              for (int q = 0; q < 8; ++q)
-                if (s[q] <= trk.thr) trk.push(s[q], col + 8 * g + q, my_idx, my_val);
+            for (int g = 0; g < 8; ++g) {
+              const float4 w4 = __ldg(wn4 + g);
+              const float sv[4] = {fmaf(-2.f, __uint_as_float(r[4 * g + 0]), w4.x),
+                                   fmaf(-2.f, __uint_as_float(r[4 * g + 1]), w4.y),
+                                   fmaf(-2.f, __uint_as_float(r[4 * g + 2]), w4.z),
+                                   fmaf(-2.f, __uint_as_float(r[4 * g + 3]), w4.w)};
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (sv[q] <= trk.thr) trk.offer(sv[q], col + 4 * g + q, my_idx, my_val);
             }
           }
         }

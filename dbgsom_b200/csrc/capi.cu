@@ -112,11 +112,11 @@ int dbgsom_bmu(const dbgsom_bmu_args* a, void* stream) {
 size_t dbgsom_accumulate_workspace_bytes(int64_t N, int32_t M) { return accumulate_workspace_bytes(N, M); }
 
 int dbgsom_accumulate(const dbgsom_accumulate_args* a, void* stream) {
-  if (!a || !a->d_X || !a->d_bmu || !a->d_W32 || !a->d_part || !a->d_workspace) return DBGSOM_E_BADARG;
+  if (!a || !a->d_X || !a->d_bmu || !a->d_W || !a->d_part || !a->d_workspace) return DBGSOM_E_BADARG;
   if (a->N <= 0 || a->D <= 0 || a->M <= 0 || a->ldx < a->D || !(a->inv_total_variance == a->inv_total_variance))
     return DBGSOM_E_BADARG;
   if (a->N > 0x7fffffffLL) return DBGSOM_E_UNSUPPORTED;  // int32 permutation
-  if (a->D % 4 != 0 || a->ldx % 4 != 0 || !aligned16(a->d_X) || !aligned16(a->d_W32)) return DBGSOM_E_UNSUPPORTED;
+  if (a->D % 4 != 0 || a->ldx % 4 != 0 || !aligned16(a->d_X) || !aligned16(a->d_W)) return DBGSOM_E_UNSUPPORTED;
   if (a->workspace_bytes < accumulate_workspace_bytes(a->N, a->M)) return DBGSOM_E_WORKSPACE;
   return run_accumulate(*a, as_stream(stream));
 }

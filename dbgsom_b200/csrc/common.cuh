@@ -61,17 +61,20 @@ __device__ __forceinline__ float4 ld_stream_f4(const float* p) {
 // ---------------------------------------------------------------------------------------------
 // Candidate tracking shared by both BMU front ends.
 //
-// One thread owns one sample row and visits the approximate scores s~_j of all prototypes in
-// ascending j.  With m = the NB-th smallest score seen so far, a prototype is a candidate when
-// s~_j <= accept(m), where accept() widens m by the error bound of the front end (both the
-// candidate's and the incumbent's score may be off by the bound).  Because accept(m) only
-// shrinks as m shrinks, testing against the running value keeps a superset of the final set;
-// stale entries are filtered at the end.  The kMaxCand smallest accepted entries live in a small
-// table in shared memory; `evicted` remembers the best score that did not fit, so an entry that
-// would still qualify at the end but was dropped is detected (-> overflow, the sample is
-// re-scored against all prototypes).
+// One thread owns one sample row and sees the approximate scores s~_j of all prototypes tile by
+// tile (ascending j).  With m = the NB-th smallest score seen so far, a prototype is a candidate
+// when s~_j <= accept(m), where accept() widens m by the error bound of the front end (both the
+// candidate's and the incumbent's score may be off by the bound).  Per tile the owner first
+// folds the tile's smallest scores into m (`observe`, branch-free), then offers the elements
+// that pass accept(m) (`offer`).  Updating m BEFORE offering matters: prototypes are stored in
+// map order, so on a smooth map the scores fall monotonically towards the best region and a
+// per-element running minimum would accept almost every element on the way down.  accept(m)
+// only shrinks as m shrinks, so offering against the current value keeps a superset of the
+// final set; stale entries are filtered in `finish`.  The kMaxCand smallest accepted entries
+// live in a small table in shared memory; `evicted` remembers the best score that did not fit,
+// so an entry that would still qualify at the end but was dropped is detected (-> overflow).
 //
-// Bound model: accept(m) = (sqrt(max(m,0)) * (1 + rel) + abs_d)^2   when sq_domain (scores are
+// Bound model: accept(m) = (sqrt(max(m,0)) * (1 + rel) + abs_d)^2   when SQ_DOMAIN (scores are
 // squared distances with a relative error `rel` and a distance-domain slack abs_d), or
 // accept(m) = m + abs_s (scores with an absolute error bound abs_s / 2).
 // ---------------------------------------------------------------------------------------------
@@ -103,17 +106,23 @@ struct RowTracker {
     }
     return m + b.abs_s;
   }
-  // slow path: called only when s <= thr.  The ring keeps the kMaxCand smallest scores seen.
-  __device__ __forceinline__ void push(float s, int j, int* ring_idx, float* ring_val) {
+  // fold the two smallest scores of a tile (a1 <= a2; a2 unused when NB == 1) into the running minima
+  __device__ __forceinline__ void observe(float a1, float a2) {
+    if (NB == 2) m2 = fminf(fmaxf(m1, a1), fminf(m2, a2));
+    m1 = fminf(m1, a1);
+    thr = accept(NB == 1 ? m1 : m2);
+  }
+  // called only for s <= thr.  The table keeps the kMaxCand smallest scores offered.
+  __device__ __forceinline__ void offer(float s, int j, int* tab_idx, float* tab_val) {
     if (n_app < (uint32_t)kMaxCand) {
-      ring_idx[n_app] = j;
-      ring_val[n_app] = s;
+      tab_idx[n_app] = j;
+      tab_val[n_app] = s;
     } else {
       int worst = 0;
-      float wv = ring_val[0];
+      float wv = tab_val[0];
 #pragma unroll
       for (int q = 1; q < kMaxCand; ++q) {
-        const float v = ring_val[q];
+        const float v = tab_val[q];
         if (v > wv) {
           wv = v;
           worst = q;
@@ -121,30 +130,23 @@ struct RowTracker {
       }
       if (s < wv) {
         evicted = fminf(evicted, wv);
-        ring_idx[worst] = j;
-        ring_val[worst] = s;
+        tab_idx[worst] = j;
+        tab_val[worst] = s;
       } else {
         evicted = fminf(evicted, s);
       }
     }
     ++n_app;
-    if (s < m1) {
-      m2 = m1;
-      m1 = s;
-    } else if (s < m2) {
-      m2 = s;
-    }
-    thr = accept(NB == 1 ? m1 : m2);
   }
   // final: compact valid candidates to out_idx[0..count) ; returns count or DBGSOM_CAND_OVERFLOW
-  __device__ __forceinline__ int finish(const int* ring_idx, const float* ring_val, int* out_idx,
+  __device__ __forceinline__ int finish(const int* tab_idx, const float* tab_val, int* out_idx,
                                         int* best_idx) const {
     const int have = n_app < (uint32_t)kMaxCand ? (int)n_app : kMaxCand;
     int cnt = 0, bi = -1;
     float bv = __int_as_float(0x7f800000);
     for (int q = 0; q < have; ++q) {
-      const float v = ring_val[q];
-      const int j = ring_idx[q];
+      const float v = tab_val[q];
+      const int j = tab_idx[q];
       if (v <= thr) {
         out_idx[cnt++] = j;
         if (v < bv || (v == bv && j < bi)) {

@@ -389,7 +389,6 @@ class DeviceEngine:
             mpad = self._prepare_w(W, m, tensor, n_pass == 3)
         ws_bytes = self.lib.dbgsom_bmu_workspace_bytes(n, n_bmu)
         ws = self._workspace("bmu", ws_bytes)
-        self.bmu_stats.zero_()
         a = nat.BmuArgs()
         a.d_X, a.N, a.D, a.ldx, a.ld16 = X.data_ptr(), n, self.ldx, ldx, self.ld16
         if tensor:
@@ -409,7 +408,7 @@ class DeviceEngine:
             nat.check(self.lib.dbgsom_bmu_candidates(a, self._stream()), "dbgsom_bmu_candidates")
         with self._Phase(self, "bmu_resolve"):
             nat.check(self.lib.dbgsom_bmu_resolve(a, self._stream()), "dbgsom_bmu_resolve")
-        self.launches += 3  # stats memset + candidate kernel + re-score kernel
+        self.launches += 2  # candidate kernel + re-score kernel
         self.last_backend = (be, n_pass)
 
     def epoch(self, sigma: float, pack_rows: bool, entropy_error: bool, _force_simt: bool = False) -> dict:
@@ -430,7 +429,7 @@ class DeviceEngine:
             use_hist = entropy_error and self.labels is not None
             acc = nat.AccumulateArgs()
             acc.d_X, acc.N, acc.D, acc.ldx = self.X.data_ptr(), self.N, self.ldx, self.ldx
-            acc.d_bmu, acc.d_W32, acc.M = idx.data_ptr(), self.W32.data_ptr(), m
+            acc.d_bmu, acc.d_W, acc.M = idx.data_ptr(), cur.data_ptr(), m
             acc.inv_total_variance = 1.0 / self.total_variance if self.total_variance > 0 else float("inf")
             acc.d_part = part.data_ptr()
             acc.d_labels = self.labels.data_ptr() if use_hist else None
@@ -478,8 +477,11 @@ class DeviceEngine:
             self.last_bmu_stats = None
             return {"error": err, "counts": counts, "change": change}
 
-    def bmu_stats_host(self) -> dict:
+    def bmu_stats_host(self, reset: bool = True) -> dict:
+        """Cumulative re-score statistics of all BMU searches since the last reset."""
         s = self.bmu_stats.cpu().numpy()
+        if reset:
+            self.bmu_stats.zero_()
         return {"ambiguous": int(s[0]), "flagged": int(s[1]), "candidates": int(s[2]), "full_rescans": int(s[3])}
 
     def bmu_train(self, n_bmu: int, previous: bool = False):

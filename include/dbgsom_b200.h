@@ -170,8 +170,8 @@ int dbgsom_bmu_resolve(const dbgsom_bmu_args* args, void* stream);
  *           neuron_activations                   :500-503
  *           numba_quantization_error             :1058-1073
  *
- * For every sample i with winner b = d_bmu[i]:  d_i = ||x_i - w_b||_2 (fp32, direct differences),
- * k_i = 1 - sqrt(1 - exp(-d_i^2 / total_variance)),
+ * For every sample i with winner b = d_bmu[i]:  d_i = ||x_i - w_b||_2 (float64, direct differences),
+ * k_i = 1 - sqrt(1 - exp(-d_i^2 / total_variance))  (float64, the reference's expression),
  *   Sk[b,:] += k_i x_i,  sk[b] += k_i,  n[b] += 1,  E[b] += d_i.
  * d_part is the contiguous float64 buffer [Sk (M*D) | sk (M) | n (M) | E (M)]; the call zeroes it
  * first.  Samples are bucketed by winner (counting sort) and each bucket is streamed once with
@@ -185,7 +185,7 @@ typedef struct dbgsom_accumulate_args {
   int32_t D;
   int64_t ldx;
   const int32_t* d_bmu;    /* [N] (stride 1) */
-  const float* d_W32;      /* [M, D] */
+  const double* d_W;       /* [M, D] float64 master prototypes */
   int32_t M;
   double inv_total_variance;
   double* d_part;          /* [M*D + 3M] */

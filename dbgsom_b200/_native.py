@@ -39,6 +39,7 @@ class BmuArgs(C.Structure):
         ("d_W16_lo", c_void_p),
         ("d_wnorm", c_void_p),
         ("d_wmax", c_void_p),
+        ("d_proto_of_col", c_void_p),
         ("scale", c_float),
         ("M", c_int32),
         ("Mpad", c_int32),
@@ -107,7 +108,7 @@ SIGNATURES = {
     "dbgsom_prepare_w": (
         c_int,
         [c_void_p, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p,
-         c_void_p, c_void_p, c_void_p],
+         c_void_p, c_void_p, c_void_p, c_void_p],
     ),
     "dbgsom_bmu_workspace_bytes": (c_size_t, [c_int64, c_int32]),
     "dbgsom_bmu": (c_int, [C.POINTER(BmuArgs), c_void_p]),

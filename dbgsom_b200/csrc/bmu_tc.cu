@@ -14,14 +14,25 @@
 // sample for the exact float64 re-score (bmu_resolve.cu).
 //
 // CTA = 128 sample rows x all prototypes, persistent over row tiles.  Warp roles:
-//   warp 0    TMA producer (one elected lane)
-//   warp 1    MMA issuer   (one elected lane; tcgen05.mma cta_group::1, M=128, N=BN, K=16)
-//   warp 2    TMEM allocate / free
-//   warps 4-7 epilogue: tcgen05.ld 32x32b -> registers -> score -> candidate tracking
+//   warp 0      TMA producer (one elected lane)
+//   warp 1      MMA issuer   (one elected lane; tcgen05.mma cta_group::1, M=128, N=BN, K=16)
+//   warp 2      TMEM allocate / free
+//   warps 4-19  epilogue: tcgen05.ld 32x32b -> registers -> score -> candidate tracking.
+//               A warp can only read the 32 TMEM lanes of its scheduler quarter (warp % 4), so four
+//               warps share each quarter and take every fourth 32-column chunk: one warp per
+//               scheduler runs at IPC ~0.06 (measured), four hide each other's latencies.  The four
+//               trackers of a row share their running minimum through shared memory and are merged
+//               at the end of the row tile.
+// Prototypes are visited in a fixed pseudo-random order (the shadow rows are permuted by
+// dbgsom_prepare_w): in map order a smooth map makes the scores fall monotonically towards the
+// best region, so nearly every chunk would set a new running minimum; in random order only
+// ~ln(#chunks) do.
 // Pipelines: smem ring full/empty (TMA <-> MMA), TMEM double buffer full/empty (MMA <-> epilogue),
 // and, when the whole K extent of the sample tile fits (XRES), a resident A tile loaded once per
 // row tile so that only prototypes stream from L2.
 #include <cuda.h>
+
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -33,8 +44,12 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // fp16 elements = one 128-byte swizzle atom row
 constexpr int UMMA_K = 16;
 constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KB
-constexpr int TC_THREADS = 256;
 constexpr int EPI_WARP0 = 4;
+constexpr int EPI_SUBS = 4;   // epilogue warps per TMEM lane quarter
+constexpr int EPI_WARPS = 4 * EPI_SUBS;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int TC_THREADS = (EPI_WARP0 + EPI_WARPS) * 32;  // 640
+constexpr int KSUB = 4;       // candidate slots per (row, epilogue warp)
 constexpr int MAX_RES_KB = 4;  // resident A up to D = 256
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -49,17 +64,19 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait suspends the thread in hardware up to the time hint (ns) instead of spinning, so the
+// single-lane producer / MMA warps do not steal issue slots from the epilogue warp of their SMSP.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra WAIT_DONE;\n"
       "bra WAIT_LOOP;\n"
       "WAIT_DONE:\n"
       "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "r"(parity), "r"(20000u)
       : "memory");
 }
 __device__ __forceinline__ bool elect_one() {
@@ -127,20 +144,52 @@ __host__ __device__ constexpr uint32_t instr_desc_f16(int m, int n) {
   return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// Keep the K smallest offered scores of one row in a small shared-memory table; `evicted` is the
+// best score that did not fit (see RowTracker in common.cuh).  Rare, hence not inlined.
+template <int K>
+__device__ __noinline__ void table_offer(float s, int col, int* tab_idx, float* tab_val, int& n_app, float& evicted) {
+  if (n_app < K) {
+    tab_idx[n_app] = col;
+    tab_val[n_app] = s;
+  } else {
+    int worst = 0;
+    float wv = tab_val[0];
+#pragma unroll
+    for (int q = 1; q < K; ++q) {
+      const float v = tab_val[q];
+      if (v > wv) {
+        wv = v;
+        worst = q;
+      }
+    }
+    if (s < wv) {
+      evicted = fminf(evicted, wv);
+      tab_idx[worst] = col;
+      tab_val[worst] = s;
+    } else {
+      evicted = fminf(evicted, s);
+    }
+  }
+  ++n_app;
+}
+
 // ------------------------------------------------------------------------------------------ layout
-template <int NPASS, int BN, bool XRES>
+// RES_KB: k-blocks of the sample tile kept resident (0 = samples stream through the ring as well)
+template <int NPASS, int BN, int RES_KB>
 struct Cfg {
+  static constexpr bool XRES = RES_KB > 0;
   static constexpr int NA = NPASS == 3 ? 2 : 1;  // hi (+ lo) tiles per operand
   static constexpr int B_TILE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = NA * B_TILE_BYTES + (XRES ? 0 : NA * A_TILE_BYTES);
-  static constexpr int RES_BYTES = XRES ? MAX_RES_KB * NA * A_TILE_BYTES : 0;
-  static constexpr int RING_BYTES = BM * kMaxCand * 8 + BM * (BN / 32) * 4;  // candidate tables + chunk minima
+  static constexpr int RES_BYTES = RES_KB * NA * A_TILE_BYTES;
+  // candidate tables [row][sub][KSUB] (idx + val), shared running minima [row], merge states [row][sub][4]
+  static constexpr int RING_BYTES = BM * EPI_SUBS * KSUB * 8 + BM * 4 + BM * EPI_SUBS * 16;
   static constexpr int MISC_BYTES = 1024;  // barriers + tmem pointer
   static constexpr int SMEM_BUDGET = 227 * 1024 - 1024;  // minus alignment slack
   static constexpr int STAGES_RAW = (SMEM_BUDGET - RES_BYTES - RING_BYTES - MISC_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int SMEM_BYTES = RES_BYTES + STAGES * STAGE_BYTES + RING_BYTES + MISC_BYTES + 1024;
-  static constexpr int TMEM_COLS = 2 * BN;  // two accumulator buffers (256 or 512 columns)
+  static constexpr int TMEM_COLS = 2 * BN;  // two accumulator buffers (128, 256 or 512 columns)
   static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
 };
 
@@ -151,24 +200,27 @@ struct Barriers {
   uint32_t tmem_base;
 };
 
-template <int NPASS, int NB, int BN, bool XRES>
+template <int NPASS, int NB, int BN, int RES_KB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     bmu_cand_tensor_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                            const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
                            int64_t N, int KB, int NT, const float* __restrict__ wnorm,
-                           const float* __restrict__ xnorm16, const float* __restrict__ wmax, float bound_coef,
+                           const int32_t* __restrict__ proto_of_col, const float* __restrict__ xnorm16,
+                           const float* __restrict__ wmax, float bound_coef,
                            int32_t* __restrict__ idx_out, int32_t* __restrict__ cand_idx,
                            uint8_t* __restrict__ cand_count) {
-  using C = Cfg<NPASS, BN, XRES>;
+  using C = Cfg<NPASS, BN, RES_KB>;
+  constexpr bool XRES = C::XRES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* res_a = smem;                               // [kb][hi|lo] A tiles (XRES)
   uint8_t* stages = smem + C::RES_BYTES;               // ring
   uint8_t* ring = stages + C::STAGES * C::STAGE_BYTES;  // candidate tables
   Barriers* bars = reinterpret_cast<Barriers*>(ring + C::RING_BYTES);
-  int* ring_idx = reinterpret_cast<int*>(ring);
-  float* ring_val = reinterpret_cast<float*>(ring + BM * kMaxCand * 4);
-  float* chunk_min = reinterpret_cast<float*>(ring + BM * kMaxCand * 8);
+  int* tab_idx = reinterpret_cast<int*>(ring);
+  float* tab_val = reinterpret_cast<float*>(ring + BM * EPI_SUBS * KSUB * 4);
+  float* row_min = reinterpret_cast<float*>(ring + BM * EPI_SUBS * KSUB * 8);
+  float4* sub_state = reinterpret_cast<float4*>(ring + BM * EPI_SUBS * KSUB * 8 + BM * 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -191,7 +243,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     mbar_init(&bars->a_empty, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&bars->tmem_full[b], 1);
-      mbar_init(&bars->tmem_empty[b], 128);
+      mbar_init(&bars->tmem_empty[b], EPI_THREADS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -290,75 +342,81 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
   } else if (warp >= EPI_WARP0) {
     // ================================================================ epilogue
-    const int t = threadIdx.x - EPI_WARP0 * 32;  // 0..127 = TMEM lane = row within the tile
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    int* my_idx = ring_idx + t * kMaxCand;
-    float* my_val = ring_val + t * kMaxCand;
-    float* my_cmin = chunk_min + t;  // [chunk][row] -> conflict-free
+    const int quarter = warp & 3;                  // TMEM lanes [32 * quarter, +32)
+    const int sub = (warp - EPI_WARP0) >> 2;       // which of the four warps of this quarter
+    const int t = quarter * 32 + lane;             // TMEM lane = row within the tile
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    int* my_idx = tab_idx + (t * EPI_SUBS + sub) * KSUB;
+    float* my_val = tab_val + (t * EPI_SUBS + sub) * KSUB;
+    constexpr int CHUNKS = BN / 32;
+    constexpr float kInf = 3.0e38f;
+    if (sub == 0) row_min[t] = kInf;
+    asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
     uint32_t acc = 0, acc_phase = 0;
     for (int64_t rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x) {
       const int64_t row = rt * BM + t;
-      RowTracker<NB, false> trk;
-      {
-        CandBound b;
-        b.rel = 0.f;
-        b.abs_d = 0.f;
-        b.abs_s = row < N ? 2.f * tensor_score_bound(xnorm16[row], wmax, bound_coef) : 0.f;
-        trk.init(b);
-      }
+      const float tau = row < N ? 2.f * tensor_score_bound(xnorm16[row], wmax, bound_coef) : 0.f;
+      float m1 = kInf, m2 = kInf, thr = kInf, evicted = __int_as_float(0x7f800000);
+      int n_app = 0;
       for (int nt = 0; nt < NT; ++nt) {
         mbar_wait(&bars->tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t tmem_acc = tmem_base + lane_base + acc * BN;
-        // pass A: smallest score(s) of the tile, per 32-column chunk (kept for pass B)
-        float a1 = __int_as_float(0x7f800000), a2 = a1;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = 0; c < CHUNKS; ++c) {
+          if (((nt * CHUNKS + c) & (EPI_SUBS - 1)) != sub) continue;  // every fourth chunk is mine
           uint32_t r[32];
           tmem_ld_32x32(tmem_acc + c * 32, r);
+          const int col = nt * BN + c * 32;
+          const float4* wn4 = reinterpret_cast<const float4*>(wnorm + col);
+          float4 w4[8];
+#pragma unroll
+          for (int g = 0; g < 8; ++g) w4[g] = __ldg(wn4 + g);
           tmem_ld_wait();
-          const float4* wn4 = reinterpret_cast<const float4*>(wnorm + nt * BN + c * 32);
-          float cm = __int_as_float(0x7f800000);
+          // pass A: smallest score(s) of the chunk
+          float a1 = kInf, a2 = kInf;
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
-            const float4 w4 = __ldg(wn4 + g);
-            const float s0 = fmaf(-2.f, __uint_as_float(r[4 * g + 0]), w4.x);
-            const float s1 = fmaf(-2.f, __uint_as_float(r[4 * g + 1]), w4.y);
-            const float s2 = fmaf(-2.f, __uint_as_float(r[4 * g + 2]), w4.z);
-            const float s3 = fmaf(-2.f, __uint_as_float(r[4 * g + 3]), w4.w);
+            const float s0 = fmaf(-2.f, __uint_as_float(r[4 * g + 0]), w4[g].x);
+            const float s1 = fmaf(-2.f, __uint_as_float(r[4 * g + 1]), w4[g].y);
+            const float s2 = fmaf(-2.f, __uint_as_float(r[4 * g + 2]), w4[g].z);
+            const float s3 = fmaf(-2.f, __uint_as_float(r[4 * g + 3]), w4[g].w);
             if (NB == 2) {
               a2 = fminf(a2, fmaxf(a1, s0)); a1 = fminf(a1, s0);
               a2 = fminf(a2, fmaxf(a1, s1)); a1 = fminf(a1, s1);
               a2 = fminf(a2, fmaxf(a1, s2)); a1 = fminf(a1, s2);
               a2 = fminf(a2, fmaxf(a1, s3)); a1 = fminf(a1, s3);
+            } else {
+              a1 = fminf(fminf(a1, fminf(s0, s1)), fminf(s2, s3));
             }
-            cm = fminf(fminf(cm, fminf(s0, s1)), fminf(s2, s3));
           }
-          my_cmin[c * BM] = cm;
-          if (NB == 1) a1 = fminf(a1, cm);
-        }
-        trk.observe(a1, a2);
-        // pass B: only chunks in which some row of this warp may hold a candidate
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          const bool mine = my_cmin[c * BM] <= trk.thr;
-          if (!__any_sync(kFullMask, mine)) continue;
-          uint32_t r[32];
-          tmem_ld_32x32(tmem_acc + c * 32, r);
-          tmem_ld_wait();
-          if (mine) {
-            const int col = nt * BN + c * 32;
-            const float4* wn4 = reinterpret_cast<const float4*>(wnorm + col);
+          // fold into the running minima; NB == 1 also shares the minimum with the other three
+          // warps of this row (a racy read-modify-write is fine: every value written is a score that
+          // was really seen, so the threshold can only be looser than necessary, never tighter)
+          if (NB == 1) {
+            const float sh = row_min[t];
+            if (a1 < sh) row_min[t] = a1;
+            m1 = fminf(m1, fminf(a1, sh));
+            thr = m1 + tau;
+          } else {
+            m2 = fminf(fmaxf(m1, a1), fminf(m2, a2));
+            m1 = fminf(m1, a1);
+            thr = m2 < 1.0e38f ? m2 + tau : kInf;
+          }
+          // pass B on the live registers: offer what is inside the bound (rare)
+          if (a1 <= thr) {
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
-              const float4 w4 = __ldg(wn4 + g);
-              const float sv[4] = {fmaf(-2.f, __uint_as_float(r[4 * g + 0]), w4.x),
-                                   fmaf(-2.f, __uint_as_float(r[4 * g + 1]), w4.y),
-                                   fmaf(-2.f, __uint_as_float(r[4 * g + 2]), w4.z),
-                                   fmaf(-2.f, __uint_as_float(r[4 * g + 3]), w4.w)};
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                if (sv[q] <= trk.thr) trk.offer(sv[q], col + 4 * g + q, my_idx, my_val);
+              const float s0 = fmaf(-2.f, __uint_as_float(r[4 * g + 0]), w4[g].x);
+              const float s1 = fmaf(-2.f, __uint_as_float(r[4 * g + 1]), w4[g].y);
+              const float s2 = fmaf(-2.f, __uint_as_float(r[4 * g + 2]), w4[g].z);
+              const float s3 = fmaf(-2.f, __uint_as_float(r[4 * g + 3]), w4[g].w);
+              if (fminf(fminf(s0, s1), fminf(s2, s3)) <= thr) {
+                if (s0 <= thr) table_offer<KSUB>(s0, col + 4 * g + 0, my_idx, my_val, n_app, evicted);
+                if (s1 <= thr) table_offer<KSUB>(s1, col + 4 * g + 1, my_idx, my_val, n_app, evicted);
+                if (s2 <= thr) table_offer<KSUB>(s2, col + 4 * g + 2, my_idx, my_val, n_app, evicted);
+                if (s3 <= thr) table_offer<KSUB>(s3, col + 4 * g + 3, my_idx, my_val, n_app, evicted);
+              }
             }
           }
         }
@@ -367,16 +425,51 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
-      if (row < N) {
-        int out[kMaxCand];
-        int best;
-        const int cnt = trk.finish(my_idx, my_val, out, &best);
-        const int valid = cnt == DBGSOM_CAND_OVERFLOW ? 0 : cnt;
+      // merge the four trackers of each row
+      sub_state[t * EPI_SUBS + sub] = make_float4(m1, m2, evicted, __int_as_float(n_app));
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
+      if (sub == 0) {
+        float g1 = kInf, g2 = kInf, ev = __int_as_float(0x7f800000);
 #pragma unroll
-        for (int q = 0; q < kMaxCand; ++q) cand_idx[row * kMaxCand + q] = q < valid ? out[q] : -1;
-        cand_count[row] = (uint8_t)cnt;
-        idx_out[row * NB] = best;
+        for (int q = 0; q < EPI_SUBS; ++q) {
+          const float4 st = sub_state[t * EPI_SUBS + q];
+          if (NB == 2) g2 = fminf(fmaxf(g1, st.x), fminf(g2, st.y));
+          g1 = fminf(g1, st.x);
+          ev = fminf(ev, st.z);
+        }
+        const float gm = NB == 1 ? g1 : g2;
+        const float gthr = gm < 1.0e38f ? gm + tau : kInf;
+        int out[kMaxCand];
+        int cnt = 0, best = -1;
+        float bv = __int_as_float(0x7f800000);
+        bool overflow = ev <= gthr;
+#pragma unroll 1
+        for (int q = 0; q < EPI_SUBS; ++q) {
+          const int have = min(__float_as_int(sub_state[t * EPI_SUBS + q].w), KSUB);
+          for (int e = 0; e < have; ++e) {
+            const float v = tab_val[(t * EPI_SUBS + q) * KSUB + e];
+            if (v <= gthr) {
+              const int jj = proto_of_col[tab_idx[(t * EPI_SUBS + q) * KSUB + e]];
+              if (cnt < kMaxCand) out[cnt] = jj;
+              ++cnt;
+              if (v < bv || (v == bv && jj < best)) {
+                bv = v;
+                best = jj;
+              }
+            }
+          }
+        }
+        if (cnt > kMaxCand) overflow = true;
+        if (row < N) {
+          const int valid = overflow ? 0 : cnt;
+#pragma unroll
+          for (int q = 0; q < kMaxCand; ++q) cand_idx[row * kMaxCand + q] = q < valid ? out[q] : -1;
+          cand_count[row] = (uint8_t)(overflow ? DBGSOM_CAND_OVERFLOW : cnt);
+          idx_out[row * NB] = best;
+        }
+        row_min[t] = kInf;
       }
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
     }
   }
 
@@ -433,9 +526,9 @@ int sm_count() {
   return n;
 }
 
-template <int NPASS, int NB, int BN, bool XRES>
+template <int NPASS, int NB, int BN, int RES_KB>
 int launch_cfg(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t s) {
-  using C = Cfg<NPASS, BN, XRES>;
+  using C = Cfg<NPASS, BN, RES_KB>;
   CUtensorMap mxh, mxl, mwh, mwl;
   int rc = make_map(&mxh, a.d_X16_hi, a.N, a.ld16, BM);
   if (rc) return rc;
@@ -450,31 +543,44 @@ int launch_cfg(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t s)
     mxl = mxh;
     mwl = mwh;
   }
-  auto kern = bmu_cand_tensor_kernel<NPASS, NB, BN, XRES>;
+  auto kern = bmu_cand_tensor_kernel<NPASS, NB, BN, RES_KB>;
   DBGSOM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   const int KB = (int)(a.ld16 / BK);
-  const int NT = ceil_div(a.M, BN);
+  const int NT = a.Mpad / BN;  // prototypes are permuted over all Mpad shadow rows
   int64_t grid = ceil_div<int64_t>(a.N, BM);
   if (grid > sm_count()) grid = sm_count();
-  kern<<<(unsigned)grid, TC_THREADS, C::SMEM_BYTES, s>>>(mxh, mxl, mwh, mwl, a.N, KB, NT, a.d_wnorm, a.d_xnorm16,
-                                                        a.d_wmax, tensor_bound_coef(NPASS, a.bound_scale), a.d_idx,
-                                                        ws.cand_idx, ws.cand_count);
+  kern<<<(unsigned)grid, TC_THREADS, C::SMEM_BYTES, s>>>(mxh, mxl, mwh, mwl, a.N, KB, NT, a.d_wnorm,
+                                                        a.d_proto_of_col, a.d_xnorm16, a.d_wmax,
+                                                        tensor_bound_coef(NPASS, a.bound_scale), a.d_idx, ws.cand_idx,
+                                                        ws.cand_count);
   DBGSOM_LAUNCH_CHECK();
   return DBGSOM_OK;
 }
 
 template <int NPASS, int NB>
 int launch_shape(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t s) {
+  // Tile shapes by shared-memory budget (227 KB): the resident sample tile takes 16 KB per k-block
+  // (x2 with the lo shadow); what is left must hold >= 4 stages of prototypes to cover TMA latency.
   const int KB = (int)(a.ld16 / BK);
-  constexpr int BN = NPASS == 1 ? 256 : 128;
-  if (KB <= MAX_RES_KB) return launch_cfg<NPASS, NB, BN, true>(a, ws, s);
-  return launch_cfg<NPASS, NB, BN, false>(a, ws, s);
+  if constexpr (NPASS == 1) {
+    if (KB <= 2) return launch_cfg<NPASS, NB, 256, 2>(a, ws, s);
+    if (KB <= MAX_RES_KB) return launch_cfg<NPASS, NB, 256, 4>(a, ws, s);
+    return launch_cfg<NPASS, NB, 256, 0>(a, ws, s);
+  } else {
+    if (KB <= 2) return launch_cfg<NPASS, NB, 128, 2>(a, ws, s);
+    if (KB <= MAX_RES_KB) {
+      static const bool bn64 = getenv("DBGSOM_TC_BN64") != nullptr;  // tuning switch
+      return bn64 ? launch_cfg<NPASS, NB, 64, 4>(a, ws, s) : launch_cfg<NPASS, NB, 128, 4>(a, ws, s);
+    }
+    return launch_cfg<NPASS, NB, 128, 0>(a, ws, s);
+  }
 }
 
 }  // namespace
 
 int launch_bmu_cand_tensor(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t s) {
   if (a.ld16 % BK != 0 || a.Mpad % 256 != 0 || a.Mpad < a.M) return DBGSOM_E_UNSUPPORTED;
+  if (!a.d_proto_of_col) return DBGSOM_E_BADARG;
   if ((reinterpret_cast<uintptr_t>(a.d_X16_hi) & 15u) || (reinterpret_cast<uintptr_t>(a.d_W16_hi) & 15u) ||
       (reinterpret_cast<uintptr_t>(a.d_wnorm) & 15u))
     return DBGSOM_E_UNSUPPORTED;

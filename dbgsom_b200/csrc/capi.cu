@@ -5,8 +5,8 @@ namespace dbgsom {
 int run_colstats(const float*, int64_t, int, int64_t, const float*, double*, cudaStream_t);
 int run_prepare_x16(const float*, int64_t, int, int64_t, const float*, float, uint16_t*, uint16_t*, int64_t, float*,
                     cudaStream_t);
-int run_prepare_w(const double*, int, int, const float*, float, float*, uint16_t*, uint16_t*, int64_t, int, float*,
-                  double*, float*, cudaStream_t);
+int run_prepare_w(const double*, int, int, const float*, float, float*, uint16_t*, uint16_t*, int64_t, int,
+                  const int32_t*, float*, double*, float*, cudaStream_t);
 int run_row_ops(double*, int, const int32_t*, int, cudaStream_t);
 int run_gather_rows(const float*, int64_t, int, const int64_t*, int, double*, cudaStream_t);
 size_t accumulate_workspace_bytes(int64_t, int);
@@ -58,12 +58,12 @@ int dbgsom_prepare_x16(const float* d_X, int64_t N, int D, int64_t ldx, const fl
 }
 
 int dbgsom_prepare_w(const double* d_W, int M, int D, const float* d_shift, float scale, float* d_W32,
-                     uint16_t* d_W16_hi, uint16_t* d_W16_lo, int64_t ld16, int Mpad, float* d_wnorm,
-                     double* d_wshift, float* d_wmax, void* stream) {
+                     uint16_t* d_W16_hi, uint16_t* d_W16_lo, int64_t ld16, int Mpad, const int32_t* d_col_of_proto,
+                     float* d_wnorm, double* d_wshift, float* d_wmax, void* stream) {
   if (!d_W || !d_W32 || !d_wmax || M <= 0 || D <= 0) return DBGSOM_E_BADARG;
   if (d_W16_hi && (!d_wnorm || !d_shift || !d_wshift || ld16 < D || Mpad < M)) return DBGSOM_E_BADARG;
-  return run_prepare_w(d_W, M, D, d_shift, scale, d_W32, d_W16_hi, d_W16_lo, ld16, Mpad, d_wnorm, d_wshift, d_wmax,
-                       as_stream(stream));
+  return run_prepare_w(d_W, M, D, d_shift, scale, d_W32, d_W16_hi, d_W16_lo, ld16, Mpad, d_col_of_proto, d_wnorm,
+                       d_wshift, d_wmax, as_stream(stream));
 }
 
 size_t dbgsom_bmu_workspace_bytes(int64_t N, int32_t n_bmu) {
@@ -79,7 +79,7 @@ static int check_bmu_args(const dbgsom_bmu_args* a) {
   if (a->want_dist && !a->d_dist) return DBGSOM_E_BADARG;
   if (a->backend != DBGSOM_BMU_SIMT && a->backend != DBGSOM_BMU_TENSOR) return DBGSOM_E_BADARG;
   if (a->backend == DBGSOM_BMU_TENSOR) {
-    if (!a->d_X16_hi || !a->d_W16_hi || !a->d_wnorm || !a->d_xnorm16) return DBGSOM_E_BADARG;
+    if (!a->d_X16_hi || !a->d_W16_hi || !a->d_wnorm || !a->d_xnorm16 || !a->d_proto_of_col) return DBGSOM_E_BADARG;
     if (a->n_pass != 1 && a->n_pass != 3) return DBGSOM_E_BADARG;
     if (a->n_pass == 3 && (!a->d_X16_lo || !a->d_W16_lo)) return DBGSOM_E_BADARG;
   }

@@ -113,7 +113,8 @@ struct RowTracker {
     thr = accept(NB == 1 ? m1 : m2);
   }
   // called only for s <= thr.  The table keeps the kMaxCand smallest scores offered.
-  __device__ __forceinline__ void offer(float s, int j, int* tab_idx, float* tab_val) {
+  // Deliberately not inlined: it is rare, and 32 inlined copies per chunk thrash the instruction cache.
+  __device__ __noinline__ void offer(float s, int j, int* tab_idx, float* tab_val) {
     if (n_app < (uint32_t)kMaxCand) {
       tab_idx[n_app] = j;
       tab_val[n_app] = s;
@@ -173,17 +174,27 @@ __host__ __device__ inline float tensor_bound_coef(int n_pass, float bound_scale
   return k * (n_pass == 1 ? 1.953125e-3f : 1.9073486e-6f);
 }
 
-// workspace layout of the BMU search: [cand_idx int32 N*kMaxCand][cand_count uint8 N (padded)]
+// workspace layout of the BMU search:
+//   [cand_idx int32 N*kMaxCand][cand_count uint8 N (padded)][rescan_count int32 (padded)][rescan_rows int32 N]
 struct BmuWorkspace {
   int32_t* cand_idx;
   uint8_t* cand_count;
+  int32_t* rescan_count;
+  int32_t* rescan_rows;
   __host__ static size_t bytes(int64_t N) {
-    return round_up<size_t>((size_t)N * kMaxCand * sizeof(int32_t), 256) + round_up<size_t>((size_t)N, 256);
+    return round_up<size_t>((size_t)N * kMaxCand * sizeof(int32_t), 256) + round_up<size_t>((size_t)N, 256) + 256 +
+           round_up<size_t>((size_t)N * sizeof(int32_t), 256);
   }
   __host__ static BmuWorkspace carve(void* base, int64_t N) {
     BmuWorkspace w;
-    w.cand_idx = reinterpret_cast<int32_t*>(base);
-    w.cand_count = reinterpret_cast<uint8_t*>(base) + round_up<size_t>((size_t)N * kMaxCand * sizeof(int32_t), 256);
+    uint8_t* p = reinterpret_cast<uint8_t*>(base);
+    w.cand_idx = reinterpret_cast<int32_t*>(p);
+    p += round_up<size_t>((size_t)N * kMaxCand * sizeof(int32_t), 256);
+    w.cand_count = p;
+    p += round_up<size_t>((size_t)N, 256);
+    w.rescan_count = reinterpret_cast<int32_t*>(p);
+    p += 256;
+    w.rescan_rows = reinterpret_cast<int32_t*>(p);
     return w;
   }
 };

@@ -104,9 +104,11 @@ __global__ void __launch_bounds__(128) prepare_w_kernel(const double* __restrict
                                                        const double* __restrict__ wshift, float scale,
                                                        float* __restrict__ W32, __half* __restrict__ W16_hi,
                                                        __half* __restrict__ W16_lo, int64_t ld16,
+                                                       const int32_t* __restrict__ col_of_proto,
                                                        float* __restrict__ wnorm, float* __restrict__ wmax) {
   __shared__ double red[3][4];
   const int j = blockIdx.x;
+  const int64_t col = col_of_proto ? col_of_proto[j] : j;  // shadow position of prototype (or padding) j
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double nu = 0.0, nr = 0.0, uv = 0.0;
   float uinf = 0.f;
@@ -124,19 +126,19 @@ __global__ void __launch_bounds__(128) prepare_w_kernel(const double* __restrict
         uv = fma(u, v, uv);
         uinf = fmaxf(uinf, fabsf((float)u));
         const __half h = __float2half_rn(fminf(fmaxf((float)u, -65504.f), 65504.f));
-        W16_hi[(int64_t)j * ld16 + d] = h;
-        if (W16_lo) W16_lo[(int64_t)j * ld16 + d] = __float2half_rn((float)(u - (double)__half2float(h)));
+        W16_hi[col * ld16 + d] = h;
+        if (W16_lo) W16_lo[col * ld16 + d] = __float2half_rn((float)(u - (double)__half2float(h)));
       }
     }
     if (W16_hi)
       for (int64_t d = D + threadIdx.x; d < ld16; d += 128) {
-        W16_hi[(int64_t)j * ld16 + d] = zero;
-        if (W16_lo) W16_lo[(int64_t)j * ld16 + d] = zero;
+        W16_hi[col * ld16 + d] = zero;
+        if (W16_lo) W16_lo[col * ld16 + d] = zero;
       }
   } else if (W16_hi) {
     for (int64_t d = threadIdx.x; d < ld16; d += 128) {
-      W16_hi[(int64_t)j * ld16 + d] = zero;
-      if (W16_lo) W16_lo[(int64_t)j * ld16 + d] = zero;
+      W16_hi[col * ld16 + d] = zero;
+      if (W16_lo) W16_lo[col * ld16 + d] = zero;
     }
   }
   nu = warp_sum(nu);
@@ -156,7 +158,7 @@ __global__ void __launch_bounds__(128) prepare_w_kernel(const double* __restrict
     nr = red[1][0] + red[1][1] + red[1][2] + red[1][3];
     uv = red[2][0] + red[2][1] + red[2][2] + red[2][3];
     const double bias = nu + 2.0 * uv;
-    if (wnorm) wnorm[j] = j < M ? (float)bias : __int_as_float(0x7f800000);
+    if (wnorm) wnorm[col] = j < M ? (float)bias : __int_as_float(0x7f800000);
     if (j < M) {
       // round up so the stored maxima are upper bounds
       atomicMax(reinterpret_cast<int*>(wmax + 0), __float_as_int(__double2float_ru(sqrt(nu))));
@@ -213,8 +215,8 @@ int run_prepare_x16(const float* X, int64_t N, int D, int64_t ldx, const float* 
 }
 
 int run_prepare_w(const double* W, int M, int D, const float* shift, float scale, float* W32, uint16_t* W16_hi,
-                  uint16_t* W16_lo, int64_t ld16, int Mpad, float* wnorm, double* wshift, float* wmax,
-                  cudaStream_t s) {
+                  uint16_t* W16_lo, int64_t ld16, int Mpad, const int32_t* col_of_proto, float* wnorm, double* wshift,
+                  float* wmax, cudaStream_t s) {
   DBGSOM_CUDA_TRY(cudaMemsetAsync(wmax, 0, 4 * sizeof(float), s));
   if (W16_hi) {
     if (!wshift) return DBGSOM_E_BADARG;
@@ -223,7 +225,8 @@ int run_prepare_w(const double* W, int M, int D, const float* shift, float scale
   }
   const int rows = W16_hi ? (Mpad > M ? Mpad : M) : M;
   prepare_w_kernel<<<rows, 128, 0, s>>>(W, M, D, shift, wshift, scale, W32, reinterpret_cast<__half*>(W16_hi),
-                                        reinterpret_cast<__half*>(W16_lo), ld16, wnorm, wmax);
+                                        reinterpret_cast<__half*>(W16_lo), ld16, W16_hi ? col_of_proto : nullptr, wnorm,
+                                        wmax);
   DBGSOM_LAUNCH_CHECK();
   return DBGSOM_OK;
 }

@@ -361,6 +361,14 @@ class DeviceEngine:
         torch = self.torch
         mpad = _round_up(m, 256)
         if tensor:
+            if getattr(self, "_perm_mpad", None) != mpad:
+                # fixed pseudo-random visiting order of the shadow rows (see bmu_tc.cu)
+                proto_of_col = np.random.default_rng(0x5EED + mpad).permutation(mpad).astype(np.int32)
+                col_of_proto = np.empty_like(proto_of_col)
+                col_of_proto[proto_of_col] = np.arange(mpad, dtype=np.int32)
+                self.proto_of_col = torch.from_numpy(proto_of_col).to(self.dev)
+                self.col_of_proto = torch.from_numpy(col_of_proto).to(self.dev)
+                self._perm_mpad = mpad
             if self.W16_hi is None or self.W16_hi.shape[0] < mpad or (need_lo and self.W16_lo is None):
                 rows = _round_up(max(mpad, self.cap), 256)
                 self.W16_hi = torch.zeros((rows, self.ld16), dtype=torch.float16, device=self.dev)
@@ -371,7 +379,8 @@ class DeviceEngine:
                 W.data_ptr(), m, self.ldx, self.shift.data_ptr(), self.scale, self.W32.data_ptr(),
                 self.W16_hi.data_ptr() if tensor else None,
                 self.W16_lo.data_ptr() if (tensor and need_lo) else None,
-                self.ld16, mpad, self.wnorm.data_ptr() if tensor else None,
+                self.ld16, mpad, self.col_of_proto.data_ptr() if tensor else None,
+                self.wnorm.data_ptr() if tensor else None,
                 self.wshift.data_ptr() if tensor else None, self.wmax.data_ptr(), self._stream(),
             ),
             "dbgsom_prepare_w",
@@ -397,6 +406,7 @@ class DeviceEngine:
             a.d_W16_hi = self.W16_hi.data_ptr()
             a.d_W16_lo = self.W16_lo.data_ptr() if self.W16_lo is not None else None
             a.d_wnorm = self.wnorm.data_ptr()
+            a.d_proto_of_col = self.proto_of_col.data_ptr()
         a.d_W, a.d_W32, a.d_wmax = W.data_ptr(), self.W32.data_ptr(), self.wmax.data_ptr()
         a.scale, a.M, a.Mpad, a.n_bmu = self.scale, m, mpad, n_bmu
         a.backend, a.n_pass, a.bound_scale, a.tie_rel = be, n_pass, self.bound_scale, 0.0

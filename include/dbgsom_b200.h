@@ -87,16 +87,19 @@ int dbgsom_prepare_x16(const float* d_X, int64_t N, int D, int64_t ldx, const fl
  * With c = mean_j W[j,:] (written to d_wshift, float64 [D]), u_j = (w_j - c) * scale and
  * v = (c - shift) * scale:  W16_hi + W16_lo ~= u_j,  d_wnorm[j] = ||u_j||^2 + 2 u_j.v, so that
  * d_wnorm[j] - 2 x'.u_j equals ||x' - (w_j - shift) * scale||^2 up to a per-sample constant.
- * d_W16_hi/lo, d_wnorm, d_wshift may be NULL (SIMT back end).  Padding rows [M, Mpad) of W16 are
- * zeroed and their wnorm set to +inf so they can never win.  d_wmax receives
+ * d_W16_hi/lo, d_wnorm, d_wshift may be NULL (SIMT back end).  Shadow row and wnorm entry of
+ * prototype j are stored at position d_col_of_proto[j] (a permutation of [0, Mpad); NULL = identity):
+ * the tensor kernel visits prototypes in shadow order and a pseudo-random order keeps the number
+ * of running-minimum updates per sample at ~ln(M) even on a smooth map.  The Mpad - M padding
+ * positions are zeroed and their wnorm set to +inf so they can never win.  d_wmax receives
  * { max_j ||u_j||_2, max_j ||w_j||_2, max_j |wnorm_j|, max_jd |u_jd| }: the first three feed the
  * candidate error bounds; if the last reaches the fp16 range (65504) the shadow was clamped and
  * the caller must use the SIMT back end for these prototypes.
  */
 int dbgsom_prepare_w(const double* d_W, int M, int D, const float* d_shift, float scale, float* d_W32,
                      uint16_t* d_W16_hi, uint16_t* d_W16_lo, int64_t ld16, int Mpad,
-                     float* d_wnorm /*[Mpad]*/, double* d_wshift /*[D]*/, float* d_wmax /*[4]*/,
-                     void* stream);
+                     const int32_t* d_col_of_proto /*[Mpad] or NULL*/, float* d_wnorm /*[Mpad]*/,
+                     double* d_wshift /*[D]*/, float* d_wmax /*[4]*/, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K1  best-matching-unit search
@@ -134,6 +137,8 @@ typedef struct dbgsom_bmu_args {
   const uint16_t* d_W16_lo; /* [Mpad, ld16]; needed for n_pass = 3 */
   const float* d_wnorm;    /* [Mpad]; may be NULL for DBGSOM_BMU_SIMT */
   const float* d_wmax;     /* [4] from dbgsom_prepare_w */
+  const int32_t* d_proto_of_col; /* [Mpad] prototype index stored in shadow row c (tensor back end;
+                              the inverse of the map given to dbgsom_prepare_w; entries >= M are padding) */
   float scale;             /* the scale both shadows were built with */
   int32_t M;
   int32_t Mpad;

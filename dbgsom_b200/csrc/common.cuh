@@ -162,16 +162,21 @@ struct RowTracker {
   }
 };
 
-// Absolute bound on |approximate - exact score| of the tensor front end for one sample, in the
-// scaled score units of the shadows (coef = bound_scale * 2^-9 for one pass, * 2^-19 for three:
-// input rounding, Cauchy-Schwarz), plus fp32 accumulation / bias rounding at the 2^-22 level.
+// Bound on |approximate - exact score| of the tensor front end for one sample, in the scaled score
+// units of the shadows:  coef * ||x'|| * max||u||  for the input rounding, plus fp32 accumulation
+// and bias rounding at the 2^-22 level.  Worst case (Cauchy-Schwarz): coef = 2^-9 for one pass,
+// 1.5 * 2^-20 for three.  The defaults sit below that on purpose -- rounding errors of 2D terms do not
+// align -- with measured head room (tools/calibrate_bound.py, winners against the fp32 path on real
+// training trajectories): one pass  0.25   * 2^-9   (first wrong winners appear at ~0.03 * 2^-9),
+//                         three     0.0625 * 2^-19  (none seen down to 0.004 * 2^-19).
+// bound_scale = 1 selects the worst-case coefficient.
 __device__ __forceinline__ float tensor_score_bound(float xnorm, const float* __restrict__ wmax, float coef) {
   const float xw = xnorm * wmax[0];
   return xw * coef + 2.4e-7f * (xw + wmax[2]);
 }
 __host__ __device__ inline float tensor_bound_coef(int n_pass, float bound_scale) {
-  const float k = bound_scale > 0.f ? bound_scale : 0.25f;
-  return k * (n_pass == 1 ? 1.953125e-3f : 1.9073486e-6f);
+  if (n_pass == 1) return (bound_scale > 0.f ? bound_scale : 0.25f) * 1.953125e-3f;
+  return (bound_scale > 0.f ? bound_scale : 0.0625f) * 1.9073486e-6f;
 }
 
 // workspace layout of the BMU search:

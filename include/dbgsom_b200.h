@@ -146,8 +146,9 @@ typedef struct dbgsom_bmu_args {
   int32_t n_bmu;           /* 1 or 2 */
   int32_t backend;         /* DBGSOM_BMU_SIMT / DBGSOM_BMU_TENSOR */
   int32_t n_pass;          /* tensor back end: 1 or 3 */
-  float bound_scale;       /* multiplies the rounding bound of the tensor back end;
-                              1.0 = worst-case (Cauchy-Schwarz) bound; <= 0 selects the default */
+  float bound_scale;       /* multiplies the rounding bound of the tensor back end; 1.0 = worst-case
+                              (Cauchy-Schwarz) bound; <= 0 selects the calibrated default (0.25 for
+                              one pass, 0.0625 for three, see csrc/common.cuh) */
   float tie_rel;           /* see above; <= 0 selects 1e-6 */
   int32_t strict;          /* 1: flagged samples are always re-scored against all prototypes */
   int32_t want_dist;       /* 0: winners only (training epoch); 1: also exact distances */

@@ -85,3 +85,70 @@ class OracleEngine:
 
     def close(self):
         pass
+
+
+class ShardedOracleEngine(OracleEngine):
+    """TEST-ONLY: the N > 1 host path on CPU.  Every rank holds a contiguous shard of the samples;
+    per epoch only the per-neuron partial sums [Sk | sk | n | E] are all-reduced (gloo), then every
+    rank smooths redundantly -- the same protocol the CUDA engine runs over NCCL."""
+
+    def __init__(self, comm, **kw):
+        super().__init__(**kw)
+        self.comm = comm
+
+    def _allreduce(self, arr, op="sum"):
+        import torch
+
+        t = torch.from_numpy(np.ascontiguousarray(arr))
+        self.comm.allreduce_(t, op)
+        return t.numpy()
+
+    def load_data(self, X, y, n_classes):
+        self.X, self.y, self.n_classes = X, y, n_classes
+        counts = np.zeros(self.comm.world, dtype=np.int64)
+        counts[self.comm.rank] = X.shape[0]
+        counts = self._allreduce(counts)
+        self.sample_offset = int(counts[: self.comm.rank].sum())
+        self.n_samples_global = int(counts.sum())
+        n = self.n_samples_global
+        s1 = self._allreduce(X.astype(np.float64).sum(axis=0))
+        mean = s1 / n
+        ss = self._allreduce(((X.astype(np.float64) - mean) ** 2).sum(axis=0))
+        self.total_var = float((ss / n).sum())
+        return {"n_samples": n, "total_variance": self.total_var, "std_norm": float(np.sqrt((ss / (n - 1)).sum()))}
+
+    def init_map_from_rows(self, rows, capacity):
+        rows = np.asarray(rows)
+        local = rows - self.sample_offset
+        own = (local >= 0) & (local < self.X.shape[0])
+        W = np.zeros((len(rows), self.X.shape[1]))
+        W[own] = self.X[local[own]]
+        self.W = self._allreduce(W)
+
+    def epoch(self, sigma, pack_rows, entropy_error):
+        M, D = self.W.shape
+        dist, win = O.bmu(self.X, self.W, 1)
+        k = O.sample_weights(dist, self.total_var)
+        Sk, sk, n = O.voronoi_sums(k, self.X, win, M)
+        E = O.quantization_errors(win, dist, M)
+        buf = self._allreduce(np.concatenate([Sk.ravel(), sk, n, E]))
+        Sk, sk, n, E = buf[: M * D].reshape(M, D), buf[M * D : M * D + M], buf[M * D + M : M * D + 2 * M], buf[M * D + 2 * M :]
+        live = np.flatnonzero(n > 0)
+        C = np.zeros((M, D))
+        if pack_rows:
+            C[: live.size] = Sk[live] / sk[live][:, None]
+        else:
+            C[live] = Sk[live] / sk[live][:, None]
+        W_new = O.smooth(C, n, O.neighborhood(self.hop, sigma))
+        change = float(np.sum(np.linalg.norm(self.W - W_new, axis=1)))
+        self.W_prev, self.W = self.W, W_new
+        if entropy_error:
+            hist = np.bincount(win * self.n_classes + self.y, minlength=M * self.n_classes).astype(np.float64)
+            E = class_entropy(self._allreduce(hist).reshape(M, self.n_classes))
+        return {"error": E, "counts": n, "change": change}
+
+    def allreduce_scalars(self, vals):
+        return list(self._allreduce(np.asarray(vals, dtype=np.float64)))
+
+    def allreduce_arrays(self, arrs, op="sum"):
+        return [self._allreduce(a, op) for a in arrs]

@@ -131,8 +131,12 @@ def make_shard(torch, device, n, d, k, rank, chunk=1 << 20):
 
 def cpu_reference_epoch_rate(wl, n_sample, steps, warmup):
     """Oracle (CPU restatement of the reference epoch) on a bounded row sample; returns a dict."""
+    from threadpoolctl import threadpool_limits
+
     from oracle import som_oracle as O
 
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core
+    threadpool_limits(limits=os.cpu_count())
     d, side, k = wl["d"], wl["side"], wl["k"]
     m = side * side
     X = O.gmm(n_sample, d, k, seed=0)
@@ -328,8 +332,8 @@ def run_ours(args, wl):
         line = {
             "metric": "training samples/sec/epoch", "value": value, "unit": "samples/s", "n_gpus": n_gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": scaling, "vs_baseline": None, "dtype": "f16x%d tensor cores + f64 re-score / f32 update / f64 smoothing" % n_pass
-            if be == nat.BMU_TENSOR else "f32 search + f64 re-score / f32 update / f64 smoothing",
+            "scaling": scaling, "vs_baseline": None, "dtype": "f16x%d tensor cores + f64 re-score / f64 update / f64 smoothing" % n_pass
+            if be == nat.BMU_TENSOR else "f32 search + f64 re-score / f64 update / f64 smoothing",
             "data": "synthetic",
             "config": {"workload": wl["name"], "rows_per_gpu": n_local, "rows_total": n_global, "d": d, "neurons": m,
                        "cache": "inputs (>= 10x L2) streamed from HBM every step, no flush needed"

@@ -297,23 +297,28 @@ def run_ours(args, wl):
             host.copy_(X)
             torch.cuda.synchronize(device)
             k_e2e = max(1, min(args.steps, 3))
+            eng.epoch_from_host(host, sigma_at(epoch, m), True, False)  # untimed: one-off stream / workspace setup
+            epoch += 1
             barrier()
             w0 = time.perf_counter()
+            step_ms = []
             for _ in range(k_e2e):
-                X.copy_(host, non_blocking=True)       # H2D of this step's samples
-                eng.X16_hi = None                      # shadows depend on the samples: rebuilt
-                r = eng.epoch(sigma_at(epoch, m), True, False)  # reads back error/count/change (D2H)
+                ws = time.perf_counter()
+                # H2D of this step's samples in row chunks on a copy stream; the fp16 shadow and the BMU
+                # search of a chunk run while the next one is in flight; reads back error/count/change
+                r = eng.epoch_from_host(host, sigma_at(epoch, m), True, False)
                 w_host = eng.weights()                 # D2H of the prototypes (the step's result)
                 epoch += 1
+                step_ms.append(round(1e3 * (time.perf_counter() - ws), 2))
             barrier()
             dt = time.perf_counter() - w0
             if world > 1:
                 t = torch.tensor([dt], dtype=torch.float64, device=device)
                 torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
                 dt = float(t.item())
-            e2e = {"value": n_global * k_e2e / dt, "unit": "samples/s", "steps": k_e2e,
+            e2e = {"value": n_global * k_e2e / dt, "unit": "samples/s", "steps": k_e2e, "step_ms": step_ms,
                    "h2d_bytes_per_step": int(n_local * d * 4), "d2h_bytes_per_step": int(w_host.nbytes + 8 * (3 * m + 5)),
-                   "note": "H2D of all samples from pinned host memory + fp16 shadow rebuild + epoch + D2H of prototypes, per step"}
+                   "note": "per step: H2D of all samples from pinned host memory (chunked, overlapped with the fp16 shadow rebuild and the BMU search), update, smoothing, D2H of prototypes and per-neuron error"}
             del host
         except Exception as exc:  # e.g. pinned allocation refused
             e2e = {"value": None, "unit": "samples/s", "error": repr(exc)[:200]}

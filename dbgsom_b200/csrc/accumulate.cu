@@ -10,8 +10,8 @@
 // Pipeline (all on one stream):
 //   histogram (counts per winner [+ class histogram]) -> exclusive scan (segment offsets, n_j as
 //   float64) -> scatter (sample permutation grouped by winner) -> segmented accumulate.
-// The accumulate kernel walks the permutation in fixed-size chunks; a team of warps owns a
-// chunk, keeps the current segment's float64 prototype in registers (so the exact distance
+// The accumulate kernel gives every team of warps one contiguous range of the permutation; the
+// team keeps the current segment's float64 prototype in registers (so the exact distance
 // ||x_i - w_b|| costs no extra memory traffic), accumulates k_i x_i in float64 registers and
 // flushes with float64 atomics whenever the segment changes.  Everything after the fp32 load
 // of x is float64, so the result is independent of the (atomic-ordered) permutation up to
@@ -136,12 +136,94 @@ __global__ void __launch_bounds__(SCAT_THREADS) scatter_kernel(const int32_t* __
 
 // ------------------------------------------------------------------------------------------ accumulate
 constexpr int ACC_THREADS = 256;
-constexpr int ACC_CHUNK = 128;  // sorted positions per team task
+constexpr int ACC_STAGES = 3;
+
+__device__ __forceinline__ uint32_t acc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void acc_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "ACC_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra ACC_DONE;\n"
+      "bra ACC_WAIT;\n"
+      "ACC_DONE:\n"
+      "}\n" ::"r"(acc_smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// float -> double without the XU pipe.  ncu showed the first version of this kernel bound by
+// F2F.F64.F32 (sm__inst_executed_pipe_xu at 109 % of peak: ~4 conversions per clock and SM); the
+// same value comes from two integer multiplies and two logic ops on the ALU/FMA pipes: the float's
+// exponent/mantissa field shifted right by 3 plus the bias difference (1023 - 127) << 20.  Exact
+// for normal floats; zeros and denormals come out with magnitude < 1.2e-38 instead of exactly
+// themselves, far below anything a float64 sum of the data can resolve; inputs are finite
+// (check_array), so the inf/NaN encodings never occur.
+__device__ __forceinline__ double f32_as_f64(float f) {
+  const uint32_t b = __float_as_uint(f);
+  const uint32_t t = b & 0x7fffffffu;
+  const uint32_t hi = (__umulhi(t, 0x20000000u) + 0x38000000u) | (b & 0x80000000u);
+  return __hiloint2double((int)hi, (int)(b << 29));
+}
+
+// Sum each of U per-lane values over the warp with a transposed butterfly (the number of live
+// values halves while the lane distance halves): 6 double shuffles for U = 4 instead of 20.
+// Afterwards lane l holds the total of row row_of_lane(l); every row is held by 32 / U lanes.
+template <int U>
+__device__ __forceinline__ int row_of_lane(int lane) {
+  return U == 4 ? ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1) : U == 2 ? (lane >> 4) & 1 : 0;
+}
+template <int U>
+__device__ __forceinline__ double reduce_rows(const double (&v)[U], int lane) {
+  double b;
+  if (U == 4) {
+    const bool h16 = lane & 16, h8 = lane & 8;
+    const double a0 = (h16 ? v[2] : v[0]) + __shfl_xor_sync(kFullMask, h16 ? v[0] : v[2], 16);
+    const double a1 = (h16 ? v[3] : v[1]) + __shfl_xor_sync(kFullMask, h16 ? v[1] : v[3], 16);
+    b = (h8 ? a1 : a0) + __shfl_xor_sync(kFullMask, h8 ? a0 : a1, 8);
+    b += __shfl_xor_sync(kFullMask, b, 4);
+  } else if (U == 2) {
+    const bool h16 = lane & 16;
+    b = (h16 ? v[1] : v[0]) + __shfl_xor_sync(kFullMask, h16 ? v[0] : v[1], 16);
+    b += __shfl_xor_sync(kFullMask, b, 8);
+    b += __shfl_xor_sync(kFullMask, b, 4);
+  } else {
+    b = v[0];
+#pragma unroll
+    for (int o = 16; o > 2; o >>= 1) b += __shfl_xor_sync(kFullMask, b, o);
+  }
+  b += __shfl_xor_sync(kFullMask, b, 2);
+  b += __shfl_xor_sync(kFullMask, b, 1);
+  return b;
+}
+template <int U>
+__device__ __forceinline__ int lane_of_row(int u) {
+  return U == 4 ? (u >> 1) * 16 + (u & 1) * 8 : U == 2 ? u * 16 : 0;
+}
+
+// Position of a team in the sorted sample sequence: next position, its segment, the segment's end.
+struct SegCursor {
+  int32_t p, seg, seg_end;
+  // rows of the next batch: at most U, never across a segment boundary or the end of the range
+  __device__ __forceinline__ int next_batch(const int32_t* __restrict__ offsets, int32_t p_end, int U) {
+    while (p >= seg_end) {  // skip empty segments
+      ++seg;
+      seg_end = offsets[seg + 1];
+    }
+    const int32_t lim = p_end < seg_end ? p_end : seg_end;
+    return lim - p < U ? lim - p : U;
+  }
+};
 
 // VPL : float4 per lane per row slab;  WPR : warps cooperating on one row (team size);
-// U   : rows in flight per team (their loads are issued together and their sample weights are
-//       evaluated in one go, lane u doing row u, so the float64 exp/sqrt costs 1/U per row).
-// A team handles columns [tw * 128 * VPL, (tw + 1) * 128 * VPL) of each row with warp tw.
+// U   : rows per batch (their sample weights are evaluated together, lane u doing row u, so the
+//       float64 exp/sqrt costs 1/U per row).
+// Every team owns one contiguous range of the sorted sequence.  Rows travel HBM -> shared memory by
+// 1-D bulk async copies (cp.async.bulk, one instruction per row, completion on an mbarrier) into a
+// ring of ACC_STAGES batches per team, so the copies of the next batches are in flight while the
+// current one is reduced and no registers are tied up by loads.  A team handles columns
+// [tw * 128 * VPL, (tw + 1) * 128 * VPL) of each row with warp tw.
 // All arithmetic is float64: distances by direct differences, k = 1 - sqrt(1 - exp(-d^2 / V))
 // literally as dbgsom/BaseSom.py:536-537, sums in float64 registers.
 template <int VPL, int WPR, int U>
@@ -150,6 +232,8 @@ __global__ void __launch_bounds__(ACC_THREADS) accumulate_kernel(
     const int32_t* __restrict__ offsets, const double* __restrict__ W, int M, double inv_var,
     double* __restrict__ part) {
   constexpr int TEAMS = ACC_THREADS / 32 / WPR;
+  extern __shared__ __align__(16) float rows_smem[];  // [TEAMS][ACC_STAGES][U][D]
+  __shared__ __align__(8) uint64_t full_bar[TEAMS][ACC_STAGES];
   __shared__ double red[TEAMS][2][WPR][U];  // cross-warp partial squared distances (double buffered)
 
   const int lane = threadIdx.x & 31;
@@ -158,157 +242,192 @@ __global__ void __launch_bounds__(ACC_THREADS) accumulate_kernel(
   const int tw = warp % WPR;
   const int col0 = tw * 128 * VPL + lane * 4;
   const int32_t total = offsets[M];  // samples that have a winner (== N without NaN rows)
+  const bool issuer = tw == 0 && lane == 0;
+  float* ring = rows_smem + (size_t)team * ACC_STAGES * U * D;
+  const uint32_t row_bytes = (uint32_t)D * 4u;
+
+  if (issuer) {
+    for (int s = 0; s < ACC_STAGES; ++s)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(acc_smem_u32(&full_bar[team][s])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
 
   double* __restrict__ Sk = part;
   double* __restrict__ sk = part + (int64_t)M * D;
   double* __restrict__ En = sk + 2 * (int64_t)M;
 
-  const int64_t n_tasks = ceil_div<int64_t>(total, ACC_CHUNK);
-  int parity = 0;
-  for (int64_t task = (int64_t)blockIdx.x * TEAMS + team; task < n_tasks; task += (int64_t)gridDim.x * TEAMS) {
-    const int32_t p0 = (int32_t)(task * ACC_CHUNK);
-    const int32_t p1 = p0 + ACC_CHUNK < total ? p0 + ACC_CHUNK : total;
-    // segment containing p0: largest j with offsets[j] <= p0
-    int lo = 0, hi = M;  // invariant offsets[lo] <= p0 < offsets[hi]
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (offsets[mid] <= p0) lo = mid; else hi = mid;
+  const int64_t n_teams = (int64_t)gridDim.x * TEAMS;
+  const int64_t team_id = (int64_t)blockIdx.x * TEAMS + team;
+  const int32_t p_begin = (int32_t)((int64_t)total * team_id / n_teams);
+  const int32_t p_end = (int32_t)((int64_t)total * (team_id + 1) / n_teams);
+  if (p_begin >= p_end) return;  // whole team exits together (no block-wide barrier follows)
+
+  // segment containing p_begin: largest j with offsets[j] <= p_begin
+  int lo = 0, hi = M;  // invariant offsets[lo] <= p_begin < offsets[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (offsets[mid] <= p_begin) lo = mid; else hi = mid;
+  }
+  SegCursor use{p_begin, lo, offsets[lo + 1]};  // consumer position
+  SegCursor pre = use;                          // prefetch position (runs ACC_STAGES - 1 batches ahead)
+
+  auto issue = [&](int stage) {  // all lanes advance the cursor, one lane issues the copies
+    if (pre.p >= p_end) return;
+    const int nb = pre.next_batch(offsets, p_end, U);
+    if (issuer) {
+      uint64_t* bar = &full_bar[team][stage];
+      // order the team's earlier generic-proxy reads of this slot before the async-proxy writes
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(acc_smem_u32(bar)), "r"(nb * row_bytes)
+                   : "memory");
+      for (int u = 0; u < nb; ++u) {
+        const float* src = X + (int64_t)perm[pre.p + u] * ldx;
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                acc_smem_u32(ring + ((size_t)stage * U + u) * D)),
+            "l"(src), "r"(row_bytes), "r"(acc_smem_u32(bar))
+            : "memory");
+      }
     }
-    int seg = lo;
-    int32_t seg_end = offsets[seg + 1];
+    pre.p += nb;
+  };
+#pragma unroll
+  for (int s = 0; s < ACC_STAGES - 1; ++s) issue(s);
 
-    double w[VPL][4], acc[VPL][4];
-    double run_k = 0.0, run_d = 0.0;
-    auto load_w = [&]() {
+  double w[VPL][4], acc[VPL][4];
+  double run_k = 0.0, run_d = 0.0;
+  int seg = -1;
+  auto load_w = [&](int sgm) {
+    seg = sgm;
 #pragma unroll
-      for (int v = 0; v < VPL; ++v) {
-        const int c = col0 + v * 128;
-        if (c < D) {
-          const double2 a = *reinterpret_cast<const double2*>(W + (int64_t)seg * D + c);
-          const double2 b = *reinterpret_cast<const double2*>(W + (int64_t)seg * D + c + 2);
-          w[v][0] = a.x; w[v][1] = a.y; w[v][2] = b.x; w[v][3] = b.y;
-        } else {
-          w[v][0] = w[v][1] = w[v][2] = w[v][3] = 0.0;
-        }
-        acc[v][0] = acc[v][1] = acc[v][2] = acc[v][3] = 0.0;
+    for (int v = 0; v < VPL; ++v) {
+      const int c = col0 + v * 128;
+      if (c < D) {
+        const double2 a = *reinterpret_cast<const double2*>(W + (int64_t)seg * D + c);
+        const double2 b = *reinterpret_cast<const double2*>(W + (int64_t)seg * D + c + 2);
+        w[v][0] = a.x; w[v][1] = a.y; w[v][2] = b.x; w[v][3] = b.y;
+      } else {
+        w[v][0] = w[v][1] = w[v][2] = w[v][3] = 0.0;
       }
-      run_k = 0.0;
-      run_d = 0.0;
-    };
-    auto flush = [&]() {
+      acc[v][0] = acc[v][1] = acc[v][2] = acc[v][3] = 0.0;
+    }
+    run_k = 0.0;
+    run_d = 0.0;
+  };
+  auto flush = [&]() {
 #pragma unroll
-      for (int v = 0; v < VPL; ++v) {
-        const int c = col0 + v * 128;
-        if (c < D) {
-          double* dst = Sk + (int64_t)seg * D + c;
-          atomicAdd(dst + 0, acc[v][0]);
-          atomicAdd(dst + 1, acc[v][1]);
-          atomicAdd(dst + 2, acc[v][2]);
-          atomicAdd(dst + 3, acc[v][3]);
-        }
+    for (int v = 0; v < VPL; ++v) {
+      const int c = col0 + v * 128;
+      if (c < D) {
+        double* dst = Sk + (int64_t)seg * D + c;
+        atomicAdd(dst + 0, acc[v][0]);
+        atomicAdd(dst + 1, acc[v][1]);
+        atomicAdd(dst + 2, acc[v][2]);
+        atomicAdd(dst + 3, acc[v][3]);
       }
-      if (tw == 0 && lane == 0) {
-        atomicAdd(sk + seg, run_k);
-        atomicAdd(En + seg, run_d);
-      }
-    };
-    load_w();
+    }
+    if (tw == 0 && lane == 0) {
+      atomicAdd(sk + seg, run_k);
+      atomicAdd(En + seg, run_d);
+    }
+  };
 
-    int32_t p = p0;
-    while (p < p1) {
-      if (p >= seg_end) {  // entering a new segment (skipping empty ones)
-        flush();
-        do {
-          ++seg;
-          seg_end = offsets[seg + 1];
-        } while (p >= seg_end);
-        load_w();
-      }
-      const int32_t lim = p1 < seg_end ? p1 : seg_end;
-      const int nb = lim - p < U ? lim - p : U;  // rows of this batch, all in the current segment
+  int stage = 0, parity = 0;
+  uint32_t phase = 0;
+  while (use.p < p_end) {
+    const int nb = use.next_batch(offsets, p_end, U);
+    if (use.seg != seg) {
+      if (seg >= 0) flush();
+      load_w(use.seg);
+    }
+    issue((stage + ACC_STAGES - 1) % ACC_STAGES);  // refill the slot consumed in the previous iteration
+    acc_mbar_wait(&full_bar[team][stage], phase);
+    const float* rows = ring + (size_t)stage * U * D;
 
-      float4 x[U][VPL];
+    double part_d2[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (u < nb) {
-          const int64_t r = perm[p + u];
+    for (int u = 0; u < U; ++u) {
+      double t = 0.0;
+      if (u < nb) {
 #pragma unroll
-          for (int v = 0; v < VPL; ++v) {
-            const int c = col0 + v * 128;
-            x[u][v] = c < D ? ld_stream_f4(X + r * ldx + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-      }
-      double d2[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        double t = 0.0;
-        if (u < nb) {
-#pragma unroll
-          for (int v = 0; v < VPL; ++v) {
-            const double a = (double)x[u][v].x - w[v][0], b = (double)x[u][v].y - w[v][1];
-            const double c = (double)x[u][v].z - w[v][2], e = (double)x[u][v].w - w[v][3];
+        for (int v = 0; v < VPL; ++v) {
+          const int c = col0 + v * 128;
+          if (c < D) {
+            const float4 x = *reinterpret_cast<const float4*>(rows + u * D + c);
+            const double a = f32_as_f64(x.x) - w[v][0], b = f32_as_f64(x.y) - w[v][1];
+            const double cc = f32_as_f64(x.z) - w[v][2], e = f32_as_f64(x.w) - w[v][3];
             t = fma(a, a, t);
             t = fma(b, b, t);
-            t = fma(c, c, t);
+            t = fma(cc, cc, t);
             t = fma(e, e, t);
           }
-          t = warp_sum(t);
         }
-        d2[u] = t;
       }
-      if (WPR > 1) {
-        if (lane == 0) {
+      part_d2[u] = t;
+    }
+    double my_d2 = reduce_rows<U>(part_d2, lane);  // lane l: squared distance of row row_of_lane(l)
+    if (WPR > 1) {
 #pragma unroll
-          for (int u = 0; u < U; ++u) red[team][parity][tw][u] = d2[u];
-        }
-        asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(WPR * 32));
+      for (int u = 0; u < U; ++u)
+        if (lane == lane_of_row<U>(u)) red[team][parity][tw][u] = my_d2;
+      asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(WPR * 32));
+      my_d2 = 0.0;
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          double t = 0.0;
+      for (int q = 0; q < WPR; ++q) my_d2 += red[team][parity][q][row_of_lane<U>(lane)];
+      parity ^= 1;
+    }
+    // each lane evaluates the weight and the distance of its row (32 / U lanes per row, redundantly)
+    const double my_dist = sqrt(my_d2);
+    const double my_k = 1.0 - sqrt(1.0 - exp(-inv_var * (my_dist * my_dist)));
 #pragma unroll
-          for (int q = 0; q < WPR; ++q) t += red[team][parity][q][u];
-          d2[u] = t;
-        }
-        parity ^= 1;
-      }
-      // lane u evaluates the weight and the distance of row u
-      double my_d2 = d2[0];
+    for (int u = 0; u < U; ++u) {
+      if (u < nb) {
+        const double k = __shfl_sync(kFullMask, my_k, lane_of_row<U>(u));
+        run_k += k;
+        run_d += __shfl_sync(kFullMask, my_dist, lane_of_row<U>(u));
 #pragma unroll
-      for (int u = 1; u < U; ++u)
-        if ((lane % U) == u) my_d2 = d2[u];
-      const double my_dist = sqrt(my_d2);
-      const double my_k = 1.0 - sqrt(1.0 - exp(-inv_var * (my_dist * my_dist)));
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (u < nb) {
-          const double k = __shfl_sync(kFullMask, my_k, u);
-          run_k += k;
-          run_d += __shfl_sync(kFullMask, my_dist, u);
-#pragma unroll
-          for (int v = 0; v < VPL; ++v) {
-            acc[v][0] = fma(k, (double)x[u][v].x, acc[v][0]);
-            acc[v][1] = fma(k, (double)x[u][v].y, acc[v][1]);
-            acc[v][2] = fma(k, (double)x[u][v].z, acc[v][2]);
-            acc[v][3] = fma(k, (double)x[u][v].w, acc[v][3]);
+        for (int v = 0; v < VPL; ++v) {
+          const int c = col0 + v * 128;
+          if (c < D) {
+            const float4 x = *reinterpret_cast<const float4*>(rows + u * D + c);
+            acc[v][0] = fma(k, f32_as_f64(x.x), acc[v][0]);
+            acc[v][1] = fma(k, f32_as_f64(x.y), acc[v][1]);
+            acc[v][2] = fma(k, f32_as_f64(x.z), acc[v][2]);
+            acc[v][3] = fma(k, f32_as_f64(x.w), acc[v][3]);
           }
         }
       }
-      p += nb;
     }
-    flush();
+    use.p += nb;
+    // the slot may be overwritten by the next issue(): every lane of the team is done reading it
+    if (WPR > 1)
+      asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(WPR * 32));
+    else
+      __syncwarp();
+    if (++stage == ACC_STAGES) {
+      stage = 0;
+      phase ^= 1;
+    }
   }
+  if (seg >= 0) flush();
 }
 
 template <int VPL, int WPR, int U>
 int launch_accumulate(const dbgsom_accumulate_args& a, const int32_t* perm, const int32_t* offsets, cudaStream_t s) {
   constexpr int TEAMS = ACC_THREADS / 32 / WPR;
-  int64_t blocks = ceil_div<int64_t>(ceil_div<int64_t>(a.N, ACC_CHUNK), TEAMS);
-  const int64_t cap = 148 * 8;
-  if (blocks > cap) blocks = cap;
+  const size_t smem = (size_t)TEAMS * ACC_STAGES * U * a.D * sizeof(float);
+  auto kern = accumulate_kernel<VPL, WPR, U>;
+  DBGSOM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = (int)((220 * 1024) / (smem + 2048));
+  if (per_sm > 4) per_sm = 4;
+  if (per_sm < 1) per_sm = 1;
+  int64_t blocks = 148 * per_sm;
+  const int64_t useful = ceil_div<int64_t>(ceil_div<int64_t>(a.N, 4 * U), TEAMS);  // >= 4 batches per team
+  if (blocks > useful) blocks = useful;
   if (blocks < 1) blocks = 1;
-  accumulate_kernel<VPL, WPR, U><<<(unsigned)blocks, ACC_THREADS, 0, s>>>(
-      a.d_X, a.N, a.D, a.ldx, perm, offsets, a.d_W, a.M, a.inv_total_variance, a.d_part);
+  kern<<<(unsigned)blocks, ACC_THREADS, smem, s>>>(a.d_X, a.N, a.D, a.ldx, perm, offsets, a.d_W, a.M,
+                                                  a.inv_total_variance, a.d_part);
   DBGSOM_LAUNCH_CHECK();
   return DBGSOM_OK;
 }

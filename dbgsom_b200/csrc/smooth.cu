@@ -85,27 +85,29 @@ __global__ void __launch_bounds__(256) denominator_kernel(const uint16_t* __rest
 }
 
 // ------------------------------------------------------------------------------------------ GEMM
-// W_out[i, d] = (sum_j H_ij B[j, d]) / den[i];   tile 32 (i) x 64 (d), 32-wide j steps.
-constexpr int TI = 32, TD = 64, TJ = 32;
+// W_out[i, d] = (sum_j H_ij B[j, d]) / den[i];   tile 128 (i) x 64 (d), 16-wide j steps, 8 x 4 outputs per
+// thread (6 shared-memory vector loads per 32 DFMA keeps the float64 pipe, not the LDS port, the limiter).
+constexpr int TI = 128, TD = 64, TJ = 16;
 __global__ void __launch_bounds__(256) smooth_gemm_kernel(const uint16_t* __restrict__ hop, int64_t ldh,
                                                          const double* __restrict__ lut, int lut_len,
                                                          const double* __restrict__ B, const double* __restrict__ den,
                                                          int M, int D, double* __restrict__ W_out) {
-  __shared__ double Hs[TJ][TI + 2];
-  __shared__ double Bs[TJ][TD];
+  __shared__ __align__(16) double Hs[TJ][TI];
+  __shared__ __align__(16) double Bs[TJ][TD];
   const int tid = threadIdx.x;
   const int tx = tid % 16;  // 4 columns
-  const int ty = tid / 16;  // 2 rows
+  const int ty = tid / 16;  // 8 rows
   const int i0 = blockIdx.y * TI, d0 = blockIdx.x * TD;
-  double acc[2][4] = {};
+  double acc[8][4] = {};
 
   for (int j0 = 0; j0 < M; j0 += TJ) {
-    // H tile: thread -> (i = tid / 8 ... , 4 consecutive j)
+    // H tile: 128 x 16 entries, 8 per thread: thread -> (i = tid / 2, 8 consecutive j)
     {
-      const int ii = tid / 8, jj = (tid % 8) * 4;
+      const int ii = tid >> 1, jj = (tid & 1) * 8;
+      const int i = i0 + ii;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int i = i0 + ii, j = j0 + jj + q;
+      for (int q = 0; q < 8; ++q) {
+        const int j = j0 + jj + q;
         double h = 0.0;
         if (i < M && j < M) {
           const unsigned hp = hop[(int64_t)i * ldh + j];
@@ -114,30 +116,39 @@ __global__ void __launch_bounds__(256) smooth_gemm_kernel(const uint16_t* __rest
         Hs[jj + q][ii] = h;
       }
     }
-    // B tile: 32 x 64 doubles, 8 per thread
+    // B tile: 16 x 64 doubles, 4 per thread
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < 4; ++q) {
       const int e = tid + q * 256;
       const int jj = e / TD, dd = e % TD;
       const int j = j0 + jj, d = d0 + dd;
       Bs[jj][dd] = (j < M && d < D) ? B[(int64_t)j * D + d] : 0.0;
     }
     __syncthreads();
-#pragma unroll 8
+#pragma unroll
     for (int jj = 0; jj < TJ; ++jj) {
-      const double h0 = Hs[jj][ty * 2], h1 = Hs[jj][ty * 2 + 1];
+      double h[8];
+#pragma unroll
+      for (int r = 0; r < 8; r += 2) {
+        const double2 hv = *reinterpret_cast<const double2*>(&Hs[jj][ty * 8 + r]);
+        h[r] = hv.x;
+        h[r + 1] = hv.y;
+      }
       const double2 b01 = *reinterpret_cast<const double2*>(&Bs[jj][tx * 4]);
       const double2 b23 = *reinterpret_cast<const double2*>(&Bs[jj][tx * 4 + 2]);
-      acc[0][0] = fma(h0, b01.x, acc[0][0]); acc[0][1] = fma(h0, b01.y, acc[0][1]);
-      acc[0][2] = fma(h0, b23.x, acc[0][2]); acc[0][3] = fma(h0, b23.y, acc[0][3]);
-      acc[1][0] = fma(h1, b01.x, acc[1][0]); acc[1][1] = fma(h1, b01.y, acc[1][1]);
-      acc[1][2] = fma(h1, b23.x, acc[1][2]); acc[1][3] = fma(h1, b23.y, acc[1][3]);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        acc[r][0] = fma(h[r], b01.x, acc[r][0]);
+        acc[r][1] = fma(h[r], b01.y, acc[r][1]);
+        acc[r][2] = fma(h[r], b23.x, acc[r][2]);
+        acc[r][3] = fma(h[r], b23.y, acc[r][3]);
+      }
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    const int i = i0 + ty * 2 + r;
+  for (int r = 0; r < 8; ++r) {
+    const int i = i0 + ty * 8 + r;
     if (i >= M) continue;
     const double dn = den[i];
 #pragma unroll

@@ -391,13 +391,18 @@ class DeviceEngine:
     def _run_bmu(self, X, n: int, ldx: int, x16, W, m: int, n_bmu: int, want_dist: bool, idx, dist, backend=None):
         """prepare_w + candidate search + exact re-score for samples X against prototypes W."""
         be, n_pass = self._pick_backend(n, m) if backend is None else backend
-        tensor = be == nat.BMU_TENSOR
         if W.shape[0] > self.W32.shape[0]:
             self.W32 = self.torch.zeros((W.shape[0], self.ldx), dtype=self.torch.float32, device=self.dev)
         with self._Phase(self, "prepare_w"):
-            mpad = self._prepare_w(W, m, tensor, n_pass == 3)
+            mpad = self._prepare_w(W, m, be == nat.BMU_TENSOR, n_pass == 3)
+        self._bmu_search(X, n, ldx, x16, W, m, mpad, n_bmu, want_dist, idx, dist, (be, n_pass))
+
+    def _bmu_search(self, X, n, ldx, x16, W, m, mpad, n_bmu, want_dist, idx, dist, backend, ws_key="bmu"):
+        """Candidate search + exact re-score of n sample rows (shadows of W must be current)."""
+        be, n_pass = backend
+        tensor = be == nat.BMU_TENSOR
         ws_bytes = self.lib.dbgsom_bmu_workspace_bytes(n, n_bmu)
-        ws = self._workspace("bmu", ws_bytes)
+        ws = self._workspace(ws_key, ws_bytes)
         a = nat.BmuArgs()
         a.d_X, a.N, a.D, a.ldx, a.ld16 = X.data_ptr(), n, self.ldx, ldx, self.ld16
         if tensor:
@@ -418,8 +423,55 @@ class DeviceEngine:
             nat.check(self.lib.dbgsom_bmu_candidates(a, self._stream()), "dbgsom_bmu_candidates")
         with self._Phase(self, "bmu_resolve"):
             nat.check(self.lib.dbgsom_bmu_resolve(a, self._stream()), "dbgsom_bmu_resolve")
-        self.launches += 2  # candidate kernel + re-score kernel
+        self.launches += 4  # candidate kernel, queue memset, re-score kernel, re-scan kernel
         self.last_backend = (be, n_pass)
+
+    def epoch_from_host(self, host_X, sigma: float, pack_rows: bool, entropy_error: bool,
+                        chunk_rows: int = 1 << 20) -> dict:
+        """One epoch whose samples arrive from (pinned) host memory: row chunks are copied on a side
+        stream while the previous chunk's fp16 shadow and BMU search run, so only the update pass waits
+        for the whole upload.  `host_X` is a float32 torch tensor [N, ldx] with the layout of `self.X`."""
+        torch = self.torch
+        with torch.cuda.device(self.dev):
+            if tuple(host_X.shape) != tuple(self.X.shape) or host_X.dtype != torch.float32:
+                raise ValueError("host_X must match the resident sample matrix (float32, same shape)")
+            m, cur = self.M, self.W[self.cur]
+            be = self._pick_backend(self.N, m)
+            tensor = be[0] == nat.BMU_TENSOR
+            need_lo = be[1] == 3
+            if tensor and (self.X16_hi is None or (need_lo and self.X16_lo is None)):
+                self.X16_hi = torch.empty((self.N, self.ld16), dtype=torch.float16, device=self.dev)
+                self.X16_lo = torch.empty((self.N, self.ld16), dtype=torch.float16, device=self.dev) if need_lo else None
+                self.xnorm16 = torch.empty(self.N, dtype=torch.float32, device=self.dev)
+            main = torch.cuda.current_stream(self.dev)
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream(self.dev)
+            self._copy_stream.wait_stream(main)  # earlier readers of X are done before it is overwritten
+            with self._Phase(self, "prepare_w"):
+                mpad = self._prepare_w(cur, m, tensor, need_lo)
+            idx = self.idx.view(-1)[: self.N]
+            for c0 in range(0, self.N, chunk_rows):
+                c1 = min(self.N, c0 + chunk_rows)
+                with torch.cuda.stream(self._copy_stream):
+                    self.X[c0:c1].copy_(host_X[c0:c1], non_blocking=True)
+                    ready = torch.cuda.Event()
+                    ready.record(self._copy_stream)
+                main.wait_event(ready)
+                x16 = None
+                if tensor:
+                    xh, xl, xn = self.X16_hi[c0:c1], (self.X16_lo[c0:c1] if need_lo else None), self.xnorm16[c0:c1]
+                    nat.check(
+                        self.lib.dbgsom_prepare_x16(
+                            self.X[c0:c1].data_ptr(), c1 - c0, self.ldx, self.ldx, self.shift.data_ptr(), self.scale,
+                            xh.data_ptr(), xl.data_ptr() if need_lo else None, self.ld16, xn.data_ptr(), self._stream(),
+                        ),
+                        "dbgsom_prepare_x16",
+                    )
+                    self.launches += 1
+                    x16 = (xh, xl, xn)
+                self._bmu_search(self.X[c0:c1], c1 - c0, self.ldx, x16, cur, m, mpad, 1, False, idx[c0:c1], None, be,
+                                 ws_key="bmu_chunk")
+            return self._update_and_smooth(be, idx, sigma, pack_rows, entropy_error)
 
     def epoch(self, sigma: float, pack_rows: bool, entropy_error: bool, _force_simt: bool = False) -> dict:
         """One training epoch on the resident data; returns per-neuron error, counts, change."""
@@ -433,59 +485,64 @@ class DeviceEngine:
                 x16 = (self.X16_hi, self.X16_lo, self.xnorm16)
             idx = self.idx.view(-1)[: self.N]
             self._run_bmu(self.X, self.N, self.ldx, x16, cur, m, 1, False, idx, None, backend=be)
+            return self._update_and_smooth(be, idx, sigma, pack_rows, entropy_error)
 
-            # K2
-            part = self.part[: m * self.ldx + 3 * m]
-            use_hist = entropy_error and self.labels is not None
-            acc = nat.AccumulateArgs()
-            acc.d_X, acc.N, acc.D, acc.ldx = self.X.data_ptr(), self.N, self.ldx, self.ldx
-            acc.d_bmu, acc.d_W, acc.M = idx.data_ptr(), cur.data_ptr(), m
-            acc.inv_total_variance = 1.0 / self.total_variance if self.total_variance > 0 else float("inf")
-            acc.d_part = part.data_ptr()
-            acc.d_labels = self.labels.data_ptr() if use_hist else None
-            acc.n_classes = self.n_classes if use_hist else 0
-            acc.d_class_hist = self.class_hist.data_ptr() if use_hist else None
-            ws = self._workspace("acc", self.lib.dbgsom_accumulate_workspace_bytes(self.N, m))
-            acc.d_workspace, acc.workspace_bytes = ws.data_ptr(), ws.numel()
-            with self._Phase(self, "accumulate"):
-                nat.check(self.lib.dbgsom_accumulate(acc, self._stream()), "dbgsom_accumulate")
-            self.launches += 6 + (1 if use_hist else 0)
+    def _update_and_smooth(self, be, idx, sigma: float, pack_rows: bool, entropy_error: bool) -> dict:
+        """K2 -> all-reduce -> K3 -> read-back, given the winners of the current prototypes."""
+        torch = self.torch
+        m, cur = self.M, self.W[self.cur]
+        # K2
+        part = self.part[: m * self.ldx + 3 * m]
+        use_hist = entropy_error and self.labels is not None
+        acc = nat.AccumulateArgs()
+        acc.d_X, acc.N, acc.D, acc.ldx = self.X.data_ptr(), self.N, self.ldx, self.ldx
+        acc.d_bmu, acc.d_W, acc.M = idx.data_ptr(), cur.data_ptr(), m
+        acc.inv_total_variance = 1.0 / self.total_variance if self.total_variance > 0 else float("inf")
+        acc.d_part = part.data_ptr()
+        acc.d_labels = self.labels.data_ptr() if use_hist else None
+        acc.n_classes = self.n_classes if use_hist else 0
+        acc.d_class_hist = self.class_hist.data_ptr() if use_hist else None
+        ws = self._workspace("acc", self.lib.dbgsom_accumulate_workspace_bytes(self.N, m))
+        acc.d_workspace, acc.workspace_bytes = ws.data_ptr(), ws.numel()
+        with self._Phase(self, "accumulate"):
+            nat.check(self.lib.dbgsom_accumulate(acc, self._stream()), "dbgsom_accumulate")
+        self.launches += 6 + (1 if use_hist else 0)
 
-            # the one collective of the path: per-neuron partial sums (+ class histogram)
-            with self._Phase(self, "allreduce"):
-                self.comm.allreduce_(part)
-                if use_hist:
-                    self.comm.allreduce_(self.class_hist[:m])
-
-            # K3
-            lut = np.exp(-(np.arange(self.hop_max + 1, dtype=np.float64) ** 2 / (2 * sigma**2)))
-            d_lut = torch.from_numpy(lut).to(self.dev)
-            out = self.W[self.cur ^ 1]
-            sm = nat.SmoothArgs()
-            sm.d_part, sm.d_hop, sm.ldh = part.data_ptr(), self.hop.data_ptr(), self.ldh
-            sm.d_kernel_lut, sm.lut_len = d_lut.data_ptr(), int(lut.size)
-            sm.M, sm.D, sm.pack_rows = m, self.ldx, int(bool(pack_rows))
-            sm.d_W_in, sm.d_W_out, sm.d_change = cur.data_ptr(), out.data_ptr(), self.change.data_ptr()
-            ws2 = self._workspace("smooth", self.lib.dbgsom_smooth_workspace_bytes(m, self.ldx))
-            sm.d_workspace, sm.workspace_bytes = ws2.data_ptr(), ws2.numel()
-            with self._Phase(self, "smooth"):
-                nat.check(self.lib.dbgsom_smooth(sm, self._stream()), "dbgsom_smooth")
-            self.launches += 6
-            self.cur ^= 1
-            self.n_previous_rows = m
-
-            # one small D2H (syncs): [sk | n | E | change | wmax]
-            tail = torch.cat([part[m * self.ldx :], self.change, self.wmax.double()]).cpu().numpy()
-            counts, err, change = tail[m : 2 * m], tail[2 * m : 3 * m], float(tail[3 * m])
-            if be[0] == nat.BMU_TENSOR and not tail[3 * m + 4] < 65000.0:
-                # a prototype left the fp16 range of the shadow (far outside the data hull): its
-                # scores were clamped, so redo this epoch on the fp32 path from the same state
-                self.cur ^= 1
-                return self.epoch(sigma, pack_rows, entropy_error, _force_simt=True)
+        # the one collective of the path: per-neuron partial sums (+ class histogram)
+        with self._Phase(self, "allreduce"):
+            self.comm.allreduce_(part)
             if use_hist:
-                err = class_entropy(self.class_hist[:m].cpu().numpy())
-            self.last_bmu_stats = None
-            return {"error": err, "counts": counts, "change": change}
+                self.comm.allreduce_(self.class_hist[:m])
+
+        # K3
+        lut = np.exp(-(np.arange(self.hop_max + 1, dtype=np.float64) ** 2 / (2 * sigma**2)))
+        d_lut = torch.from_numpy(lut).to(self.dev)
+        out = self.W[self.cur ^ 1]
+        sm = nat.SmoothArgs()
+        sm.d_part, sm.d_hop, sm.ldh = part.data_ptr(), self.hop.data_ptr(), self.ldh
+        sm.d_kernel_lut, sm.lut_len = d_lut.data_ptr(), int(lut.size)
+        sm.M, sm.D, sm.pack_rows = m, self.ldx, int(bool(pack_rows))
+        sm.d_W_in, sm.d_W_out, sm.d_change = cur.data_ptr(), out.data_ptr(), self.change.data_ptr()
+        ws2 = self._workspace("smooth", self.lib.dbgsom_smooth_workspace_bytes(m, self.ldx))
+        sm.d_workspace, sm.workspace_bytes = ws2.data_ptr(), ws2.numel()
+        with self._Phase(self, "smooth"):
+            nat.check(self.lib.dbgsom_smooth(sm, self._stream()), "dbgsom_smooth")
+        self.launches += 6
+        self.cur ^= 1
+        self.n_previous_rows = m
+
+        # one small D2H (syncs): [sk | n | E | change | wmax]
+        tail = torch.cat([part[m * self.ldx :], self.change, self.wmax.double()]).cpu().numpy()
+        counts, err, change = tail[m : 2 * m], tail[2 * m : 3 * m], float(tail[3 * m])
+        if be[0] == nat.BMU_TENSOR and not tail[3 * m + 4] < 65000.0:
+            # a prototype left the fp16 range of the shadow (far outside the data hull): its
+            # scores were clamped, so redo this epoch on the fp32 path from the same state
+            self.cur ^= 1
+            return self.epoch(sigma, pack_rows, entropy_error, _force_simt=True)
+        if use_hist:
+            err = class_entropy(self.class_hist[:m].cpu().numpy())
+        self.last_bmu_stats = None
+        return {"error": err, "counts": counts, "change": change}
 
     def bmu_stats_host(self, reset: bool = True) -> dict:
         """Cumulative re-score statistics of all BMU searches since the last reset."""

@@ -205,6 +205,32 @@ def test_epoch_wide_rows_and_large_maps(shape):
     assert r["counts"].sum() == n
 
 
+def test_epoch_from_host_equals_resident_epoch():
+    """The streamed-upload epoch (chunked H2D overlapped with the BMU search) gives the same result."""
+    import torch
+
+    X = _datasets.gmm(30000, 128, 16, 4)
+    W = X[:400].astype(np.float64)
+    hop = O.hop_matrix_grid(20, 20)
+    out = []
+    for streamed in (False, True):
+        e = engine(bmu_backend="tensor")
+        e.load_data(X, None, 0)
+        e.set_map(W)
+        e.set_hops(hop_u16(hop))
+        if streamed:
+            host = torch.from_numpy(X).pin_memory()
+            e.X.zero_()
+            r = e.epoch_from_host(host, 2.0, True, False, chunk_rows=7000)
+        else:
+            r = e.epoch(2.0, True, False)
+        out.append((r, e.weights()))
+        e.close()
+    np.testing.assert_array_equal(out[0][0]["counts"], out[1][0]["counts"])
+    np.testing.assert_allclose(out[0][0]["error"], out[1][0]["error"], rtol=1e-12)
+    np.testing.assert_allclose(out[0][1], out[1][1], rtol=1e-12, atol=1e-12)
+
+
 def test_epoch_entropy_error():
     X, lab = _datasets.gmm(5000, 32, 6, 3, return_labels=True)
     W = X[:25].astype(np.float64)

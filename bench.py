@@ -13,6 +13,7 @@ Workloads; `c3` is the default at every GPU count (weak
     c3     10M x 256 per GPU, 64 x 64 map           (BASELINE.json configs[2], the roofline config)
     c4     100M x 128 in total, sharded, 64 x 64    (configs[3], strong scaling)
     c2     70000 x 784, 20 x 20 map                 (configs[1]; latency-bound)
+    c5     5M x 4096 in total, sharded, 128 x 128   (configs[4] at its final map size; needs 8 GPUs or --rows)
     small  200k x 64, 16 x 16 map                   (smoke-sized)
 
 `--impl reference` times the CPU restatement of the reference's epoch (oracle/, numpy + the same
@@ -36,6 +37,7 @@ WORKLOADS = {
     "c3": dict(per_gpu=10_000_000, total=None, d=256, side=64, k=64, name="SomVQ epoch, GMM 10M x 256 per GPU, fixed 64x64 map"),
     "c4": dict(per_gpu=None, total=100_000_000, d=128, side=64, k=64, name="SomVQ epoch, GMM 100M x 128 sharded, fixed 64x64 map"),
     "c2": dict(per_gpu=70_000, total=None, d=784, side=20, k=10, name="SomClassifier-shaped epoch, GMM 70000 x 784, 20x20 map"),
+    "c5": dict(per_gpu=None, total=5_000_000, d=4096, side=128, k=64, name="SomVQ epoch, GMM 5M x 4096 sharded, fixed 128x128 map (16384 neurons)"),
     "small": dict(per_gpu=200_000, total=None, d=64, side=16, k=16, name="GMM 200k x 64, 16x16 map"),
 }
 N_ITER_SCHEDULE = 200  # sigma follows the coarse phase of a 200-epoch fit

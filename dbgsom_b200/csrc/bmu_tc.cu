@@ -118,6 +118,22 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uin
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with the A operand read from tensor memory (128 lanes = rows, 2 fp16 per 32-bit column)
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// shared memory -> tensor memory: 128 rows x 256 bit (one K = 16 slice of an fp16 operand tile)
+__device__ __forceinline__ void tc_cp_128x256b(uint32_t tmem_dst, uint64_t desc_src) {
+  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(tmem_dst), "l"(desc_src) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -175,32 +191,44 @@ __device__ __noinline__ void table_offer(float s, int col, int* tab_idx, float* 
 
 // ------------------------------------------------------------------------------------------ layout
 // RES_KB: k-blocks of the sample tile kept resident (0 = samples stream through the ring as well)
-template <int NPASS, int BN, int RES_KB>
+// ATM: the sample tile lives in TENSOR memory instead (columns [2*BN, 2*BN + 32*KB*NA)): its k-blocks pass
+//      through the ring once per row tile and are moved with tcgen05.cp; the MMA then takes A from TMEM,
+//      which leaves all shared memory to the prototype ring (5 stages instead of 2 at D = 256, 3 passes)
+//      and, for D <= 128, tensor-memory room for three accumulator buffers instead of two.
+template <int NPASS, int BN, int RES_KB, int AKB>
 struct Cfg {
+  static constexpr bool ATM = AKB > 0;  // AKB: k-blocks of the sample tile held in tensor memory
   static constexpr bool XRES = RES_KB > 0;
+  static constexpr bool ASTREAM = !XRES && !ATM;
   static constexpr int NA = NPASS == 3 ? 2 : 1;  // hi (+ lo) tiles per operand
   static constexpr int B_TILE_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = NA * B_TILE_BYTES + (XRES ? 0 : NA * A_TILE_BYTES);
+  static constexpr int STAGE_BYTES = NA * B_TILE_BYTES + (ASTREAM ? NA * A_TILE_BYTES : 0);
+  static_assert(!ATM || (RES_KB == 0 && B_TILE_BYTES == A_TILE_BYTES), "TMEM-resident A shares the ring: BN must be 128");
+  static constexpr int A_COLS = AKB * NA * (BK / 2);                 // tensor-memory columns of the sample tile
+  static constexpr int NACC = ATM ? ((512 - A_COLS) / BN > 4 ? 4 : (512 - A_COLS) / BN) : 2;  // accumulator buffers
+  static_assert(NACC >= 2, "need two accumulator buffers");
   static constexpr int RES_BYTES = RES_KB * NA * A_TILE_BYTES;
   // candidate tables [row][sub][KSUB] (idx + val), shared running minima [row], merge states [row][sub][4]
   static constexpr int RING_BYTES = BM * EPI_SUBS * KSUB * 8 + BM * 4 + BM * EPI_SUBS * 16;
   static constexpr int MISC_BYTES = 1024;  // barriers + tmem pointer
+  static constexpr int WN_SMEM_FLOATS = ATM ? 4096 : 0;  // wnorm staged in shared memory when it fits
+  static constexpr int WN_BYTES = WN_SMEM_FLOATS * 4;
   static constexpr int SMEM_BUDGET = 227 * 1024 - 1024;  // minus alignment slack
-  static constexpr int STAGES_RAW = (SMEM_BUDGET - RES_BYTES - RING_BYTES - MISC_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES_RAW = (SMEM_BUDGET - RES_BYTES - RING_BYTES - MISC_BYTES - WN_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = RES_BYTES + STAGES * STAGE_BYTES + RING_BYTES + MISC_BYTES + 1024;
-  static constexpr int TMEM_COLS = 2 * BN;  // two accumulator buffers (128, 256 or 512 columns)
+  static constexpr int SMEM_BYTES = RES_BYTES + STAGES * STAGE_BYTES + RING_BYTES + MISC_BYTES + WN_BYTES + 1024;
+  static constexpr int TMEM_COLS = ATM ? 512 : 2 * BN;  // accumulator buffers (+ the sample tile)
   static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
 };
 
 struct Barriers {
   uint64_t full[8], empty[8];
   uint64_t a_full, a_empty;
-  uint64_t tmem_full[2], tmem_empty[2];
+  uint64_t tmem_full[4], tmem_empty[4];
   uint32_t tmem_base;
 };
 
-template <int NPASS, int NB, int BN, int RES_KB>
+template <int NPASS, int NB, int BN, int RES_KB, int AKB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     bmu_cand_tensor_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                            const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
@@ -209,8 +237,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                            const float* __restrict__ wmax, float bound_coef,
                            int32_t* __restrict__ idx_out, int32_t* __restrict__ cand_idx,
                            uint8_t* __restrict__ cand_count) {
-  using C = Cfg<NPASS, BN, RES_KB>;
+  using C = Cfg<NPASS, BN, RES_KB, AKB>;
+  constexpr bool ATM = C::ATM;
+  constexpr int NACC = C::NACC;
   constexpr bool XRES = C::XRES;
+  constexpr bool ASTREAM = C::ASTREAM;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* res_a = smem;                               // [kb][hi|lo] A tiles (XRES)
@@ -221,6 +252,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   float* tab_val = reinterpret_cast<float*>(ring + BM * EPI_SUBS * KSUB * 4);
   float* row_min = reinterpret_cast<float*>(ring + BM * EPI_SUBS * KSUB * 8);
   float4* sub_state = reinterpret_cast<float4*>(ring + BM * EPI_SUBS * KSUB * 8 + BM * 4);
+  float* wn_smem = reinterpret_cast<float*>(ring + C::RING_BYTES + C::MISC_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -241,7 +273,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
     mbar_init(&bars->a_full, 1);
     mbar_init(&bars->a_empty, 1);
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < NACC; ++b) {
       mbar_init(&bars->tmem_full[b], 1);
       mbar_init(&bars->tmem_empty[b], EPI_THREADS);
     }
@@ -274,6 +306,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           }
           a_phase ^= 1;
         }
+        if (ATM) {  // the sample tile's k-blocks travel through the ring once per row tile
+          for (int kb = 0; kb < KB; ++kb) {
+            mbar_wait(&bars->empty[stage], phase ^ 1);
+            uint8_t* st = stages + stage * C::STAGE_BYTES;
+            mbar_expect_tx(&bars->full[stage], (uint32_t)(C::NA * A_TILE_BYTES));
+            tma_load_2d(st, &map_xh, &bars->full[stage], kb * BK, row0);
+            if (NPASS == 3) tma_load_2d(st + A_TILE_BYTES, &map_xl, &bars->full[stage], kb * BK, row0);
+            if (++stage == C::STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
         for (int nt = 0; nt < NT; ++nt) {
           for (int kb = 0; kb < KB; ++kb) {
             mbar_wait(&bars->empty[stage], phase ^ 1);
@@ -281,7 +326,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             mbar_expect_tx(&bars->full[stage], (uint32_t)C::STAGE_BYTES);
             tma_load_2d(st, &map_wh, &bars->full[stage], kb * BK, nt * BN);
             if (NPASS == 3) tma_load_2d(st + C::B_TILE_BYTES, &map_wl, &bars->full[stage], kb * BK, nt * BN);
-            if (!XRES) {
+            if (ASTREAM) {
               uint8_t* sa = st + C::NA * C::B_TILE_BYTES;
               tma_load_2d(sa, &map_xh, &bars->full[stage], kb * BK, row0);
               if (NPASS == 3) tma_load_2d(sa + A_TILE_BYTES, &map_xl, &bars->full[stage], kb * BK, row0);
@@ -305,6 +350,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           mbar_wait(&bars->a_full, a_phase);
           a_phase ^= 1;
         }
+        const uint32_t tmem_a = tmem_base + NACC * BN;  // ATM: [kb][k] -> 8 columns each, lo half after AKB blocks
+        if (ATM) {
+          // tcgen05.cp and tcgen05.mma execute in issue order, so these copies run after the previous row
+          // tile's MMAs have read the old sample tile and before this row tile's MMAs read the new one
+          for (int kb = 0; kb < KB; ++kb) {
+            mbar_wait(&bars->full[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(stages + stage * C::STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              tc_cp_128x256b(tmem_a + kb * (BK / 2) + k * 8, smem_desc_sw128(sa + k * UMMA_K * 2));
+              if (NPASS == 3)
+                tc_cp_128x256b(tmem_a + AKB * (BK / 2) + kb * (BK / 2) + k * 8,
+                               smem_desc_sw128(sa + A_TILE_BYTES + k * UMMA_K * 2));
+            }
+            tc_commit(&bars->empty[stage]);
+            if (++stage == C::STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
         for (int nt = 0; nt < NT; ++nt) {
           mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
           tc_fence_after();
@@ -321,10 +388,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint32_t koff = k * UMMA_K * 2;  // bytes along K inside the swizzle atom
-              tc_mma_f16(tmem_d, smem_desc_sw128(a_hi + koff), smem_desc_sw128(b_hi + koff), idesc, (kb | k) != 0);
-              if (NPASS == 3) {
-                tc_mma_f16(tmem_d, smem_desc_sw128(a_hi + koff), smem_desc_sw128(b_lo + koff), idesc, 1);
-                tc_mma_f16(tmem_d, smem_desc_sw128(a_lo + koff), smem_desc_sw128(b_hi + koff), idesc, 1);
+              if (ATM) {
+                const uint32_t ta_hi = tmem_a + kb * (BK / 2) + k * 8;
+                const uint32_t ta_lo = ta_hi + AKB * (BK / 2);
+                tc_mma_f16_ts(tmem_d, ta_hi, smem_desc_sw128(b_hi + koff), idesc, (kb | k) != 0);
+                if (NPASS == 3) {
+                  tc_mma_f16_ts(tmem_d, ta_hi, smem_desc_sw128(b_lo + koff), idesc, 1);
+                  tc_mma_f16_ts(tmem_d, ta_lo, smem_desc_sw128(b_hi + koff), idesc, 1);
+                }
+              } else {
+                tc_mma_f16(tmem_d, smem_desc_sw128(a_hi + koff), smem_desc_sw128(b_hi + koff), idesc, (kb | k) != 0);
+                if (NPASS == 3) {
+                  tc_mma_f16(tmem_d, smem_desc_sw128(a_hi + koff), smem_desc_sw128(b_lo + koff), idesc, 1);
+                  tc_mma_f16(tmem_d, smem_desc_sw128(a_lo + koff), smem_desc_sw128(b_hi + koff), idesc, 1);
+                }
               }
             }
             tc_commit(&bars->empty[stage]);  // frees the smem stage once these MMAs have read it
@@ -334,8 +411,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             }
           }
           tc_commit(&bars->tmem_full[acc]);  // accumulator complete -> epilogue
-          acc ^= 1;
-          if (acc == 0) acc_phase ^= 1;
+          if (++acc == NACC) {
+            acc = 0;
+            acc_phase ^= 1;
+          }
         }
         if (XRES) tc_commit(&bars->a_empty);  // resident A tile may be overwritten
       }
@@ -351,6 +430,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     constexpr int CHUNKS = BN / 32;
     constexpr float kInf = 3.0e38f;
     if (sub == 0) row_min[t] = kInf;
+    // wnorm is read by every row for every chunk: keep it in shared memory when it fits (global / L1
+    // loads showed up as the longest stall of the epilogue at D = 128)
+    const int mpad = NT * BN;
+    const bool wn_in_smem = C::WN_SMEM_FLOATS > 0 && mpad <= C::WN_SMEM_FLOATS;
+    if (wn_in_smem)
+      for (int i = threadIdx.x - EPI_WARP0 * 32; i < mpad; i += EPI_THREADS) wn_smem[i] = wnorm[i];
+    const float* wn_src = wn_in_smem ? wn_smem : wnorm;
     asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
     uint32_t acc = 0, acc_phase = 0;
     for (int64_t rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x) {
@@ -368,10 +454,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           uint32_t r[32];
           tmem_ld_32x32(tmem_acc + c * 32, r);
           const int col = nt * BN + c * 32;
-          const float4* wn4 = reinterpret_cast<const float4*>(wnorm + col);
+          const float4* wn4 = reinterpret_cast<const float4*>(wn_src + col);
           float4 w4[8];
 #pragma unroll
-          for (int g = 0; g < 8; ++g) w4[g] = __ldg(wn4 + g);
+          for (int g = 0; g < 8; ++g) w4[g] = wn4[g];
           tmem_ld_wait();
           // pass A: smallest score(s) of the chunk
           float a1 = kInf, a2 = kInf;
@@ -422,8 +508,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
         tc_fence_before();
         mbar_arrive(&bars->tmem_empty[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        if (++acc == NACC) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
       }
       // merge the four trackers of each row
       sub_state[t * EPI_SUBS + sub] = make_float4(m1, m2, evicted, __int_as_float(n_app));
@@ -526,9 +614,9 @@ int sm_count() {
   return n;
 }
 
-template <int NPASS, int NB, int BN, int RES_KB>
+template <int NPASS, int NB, int BN, int RES_KB, int AKB = 0>
 int launch_cfg(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t s) {
-  using C = Cfg<NPASS, BN, RES_KB>;
+  using C = Cfg<NPASS, BN, RES_KB, AKB>;
   CUtensorMap mxh, mxl, mwh, mwl;
   int rc = make_map(&mxh, a.d_X16_hi, a.N, a.ld16, BM);
   if (rc) return rc;
@@ -543,7 +631,7 @@ int launch_cfg(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t s)
     mxl = mxh;
     mwl = mwh;
   }
-  auto kern = bmu_cand_tensor_kernel<NPASS, NB, BN, RES_KB>;
+  auto kern = bmu_cand_tensor_kernel<NPASS, NB, BN, RES_KB, AKB>;
   DBGSOM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   const int KB = (int)(a.ld16 / BK);
   const int NT = a.Mpad / BN;  // prototypes are permuted over all Mpad shadow rows
@@ -567,11 +655,10 @@ int launch_shape(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t 
     if (KB <= MAX_RES_KB) return launch_cfg<NPASS, NB, 256, 4>(a, ws, s);
     return launch_cfg<NPASS, NB, 256, 0>(a, ws, s);
   } else {
-    if (KB <= 2) return launch_cfg<NPASS, NB, 128, 2>(a, ws, s);
-    if (KB <= MAX_RES_KB) {
-      static const bool bn64 = getenv("DBGSOM_TC_BN64") != nullptr;  // tuning switch
-      return bn64 ? launch_cfg<NPASS, NB, 64, 4>(a, ws, s) : launch_cfg<NPASS, NB, 128, 4>(a, ws, s);
-    }
+    static const bool a_smem = getenv("DBGSOM_TC_A_SMEM") != nullptr;  // tuning switch: sample tile in smem
+    if (KB <= 2) return a_smem ? launch_cfg<NPASS, NB, 128, 2>(a, ws, s) : launch_cfg<NPASS, NB, 128, 0, 2>(a, ws, s);
+    if (KB <= MAX_RES_KB)
+      return a_smem ? launch_cfg<NPASS, NB, 128, 4>(a, ws, s) : launch_cfg<NPASS, NB, 128, 0, 4>(a, ws, s);
     return launch_cfg<NPASS, NB, 128, 0>(a, ws, s);
   }
 }

@@ -234,6 +234,10 @@ class BaseSom(BaseEstimator):
                 entropy_error=use_entropy,
             )
             topo.error[:] = result["error"]
+            if not np.isfinite(result["change"]):
+                # A neuron farther than ~38 sigma hops from every live one gets 0/0 prototypes (SURVEY.md
+                # quirk Q10); the reference then fails in its next `kneighbors` call with the same error.
+                raise ValueError("Input X contains NaN (a prototype became NaN during neighbourhood smoothing).")
             if result["change"] < self.convergence_treshold:
                 self.converged_ = True  # a latch, like the reference (quirk Q7)
             if self.converged_ and self._training_phase == "fine":

@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(SCAT_THREADS) scatter_kernel(const int32_t* __
 
 // ------------------------------------------------------------------------------------------ accumulate
 constexpr int ACC_THREADS = 256;
-constexpr int ACC_STAGES = 3;
+constexpr int ACC_STAGES = 2;
 
 __device__ __forceinline__ uint32_t acc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void acc_mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -355,7 +355,9 @@ __global__ void __launch_bounds__(ACC_THREADS) accumulate_kernel(
           const int c = col0 + v * 128;
           if (c < D) {
             const float4 x = *reinterpret_cast<const float4*>(rows + u * D + c);
-            const double a = f32_as_f64(x.x) - w[v][0], b = f32_as_f64(x.y) - w[v][1];
+            // one conversion in four goes through the XU pipe (F2F, ~27 clk per warp instruction, otherwise
+            // idle), the rest through the ALU/FMA pipes: neither saturates
+            const double a = (double)x.x - w[v][0], b = f32_as_f64(x.y) - w[v][1];
             const double cc = f32_as_f64(x.z) - w[v][2], e = f32_as_f64(x.w) - w[v][3];
             t = fma(a, a, t);
             t = fma(b, b, t);

@@ -186,7 +186,7 @@ def run_reference(args, wl):
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=args.out)
 
 
 # ---------------------------------------------------------------------------------------------- ours
@@ -353,10 +353,19 @@ def run_ours(args, wl):
             "phases_ms": {k_: mean(v) for k_, v in phases.items()},
             "bmu_rescore_per_epoch": {k_: v / args.steps for k_, v in bmu_stats.items()}, "last_change": out["change"],
         }
-        print(json.dumps(line))
+        print(json.dumps(line), file=args.out)
     eng.close()
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+def _stdout_for_json_only():
+    """Send everything libraries write to fd 1 (e.g. NCCL's version banner) to stderr; return a file for
+    the one JSON line the driver parses."""
+    sys.stdout.flush()
+    keep = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(keep, "w")
 
 
 def main():
@@ -373,10 +382,12 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     wl = WORKLOADS[args.workload]
+    args.out = _stdout_for_json_only()
     if args.impl == "reference":
         run_reference(args, wl)
     else:
         run_ours(args, wl)
+    args.out.flush()
 
 
 if __name__ == "__main__":

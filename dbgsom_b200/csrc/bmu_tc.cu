@@ -160,27 +160,35 @@ __host__ __device__ constexpr uint32_t instr_desc_f16(int m, int n) {
   return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-// Keep the K smallest offered scores of one row in a small shared-memory table; `evicted` is the
-// best score that did not fit (see RowTracker in common.cuh).  Rare, hence not inlined.
+// Keep the K smallest offered (score, prototype index) pairs of one row in a small shared-memory table;
+// `evicted` is the best score that did not fit (see RowTracker in common.cuh).  Equal scores are ordered
+// by prototype index, so among exact duplicates -- identical shadows give bit-identical scores -- the
+// lowest index always survives, which is the tie rule of the reference (sklearn/utils/_heap.pyx:46).
+// Rare, hence not inlined.
 template <int K>
-__device__ __noinline__ void table_offer(float s, int col, int* tab_idx, float* tab_val, int& n_app, float& evicted) {
+__device__ __noinline__ void table_offer(float s, int col, const int32_t* __restrict__ proto_of_col, int* tab_idx,
+                                         float* tab_val, int& n_app, float& evicted) {
+  const int j = proto_of_col[col];
   if (n_app < K) {
-    tab_idx[n_app] = col;
+    tab_idx[n_app] = j;
     tab_val[n_app] = s;
   } else {
     int worst = 0;
     float wv = tab_val[0];
+    int wj = tab_idx[0];
 #pragma unroll
     for (int q = 1; q < K; ++q) {
       const float v = tab_val[q];
-      if (v > wv) {
+      const int jq = tab_idx[q];
+      if (v > wv || (v == wv && jq > wj)) {
         wv = v;
+        wj = jq;
         worst = q;
       }
     }
-    if (s < wv) {
+    if (s < wv || (s == wv && j < wj)) {
       evicted = fminf(evicted, wv);
-      tab_idx[worst] = col;
+      tab_idx[worst] = j;
       tab_val[worst] = s;
     } else {
       evicted = fminf(evicted, s);
@@ -498,10 +506,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
               const float s2 = fmaf(-2.f, __uint_as_float(r[4 * g + 2]), w4[g].z);
               const float s3 = fmaf(-2.f, __uint_as_float(r[4 * g + 3]), w4[g].w);
               if (fminf(fminf(s0, s1), fminf(s2, s3)) <= thr) {
-                if (s0 <= thr) table_offer<KSUB>(s0, col + 4 * g + 0, my_idx, my_val, n_app, evicted);
-                if (s1 <= thr) table_offer<KSUB>(s1, col + 4 * g + 1, my_idx, my_val, n_app, evicted);
-                if (s2 <= thr) table_offer<KSUB>(s2, col + 4 * g + 2, my_idx, my_val, n_app, evicted);
-                if (s3 <= thr) table_offer<KSUB>(s3, col + 4 * g + 3, my_idx, my_val, n_app, evicted);
+                if (s0 <= thr) table_offer<KSUB>(s0, col + 4 * g + 0, proto_of_col, my_idx, my_val, n_app, evicted);
+                if (s1 <= thr) table_offer<KSUB>(s1, col + 4 * g + 1, proto_of_col, my_idx, my_val, n_app, evicted);
+                if (s2 <= thr) table_offer<KSUB>(s2, col + 4 * g + 2, proto_of_col, my_idx, my_val, n_app, evicted);
+                if (s3 <= thr) table_offer<KSUB>(s3, col + 4 * g + 3, proto_of_col, my_idx, my_val, n_app, evicted);
               }
             }
           }
@@ -537,7 +545,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           for (int e = 0; e < have; ++e) {
             const float v = tab_val[(t * EPI_SUBS + q) * KSUB + e];
             if (v <= gthr) {
-              const int jj = proto_of_col[tab_idx[(t * EPI_SUBS + q) * KSUB + e]];
+              const int jj = tab_idx[(t * EPI_SUBS + q) * KSUB + e];
               if (cnt < kMaxCand) out[cnt] = jj;
               ++cnt;
               if (v < bv || (v == bv && jj < best)) {

@@ -112,8 +112,9 @@ struct RowTracker {
     m1 = fminf(m1, a1);
     thr = accept(NB == 1 ? m1 : m2);
   }
-  // called only for s <= thr.  The table keeps the kMaxCand smallest scores offered.
-  // Deliberately not inlined: it is rare, and 32 inlined copies per chunk thrash the instruction cache.
+  // called only for s <= thr.  The table keeps the kMaxCand smallest (score, index) pairs offered; equal
+  // scores are ordered by index so the lowest index among exact duplicates always survives.
+  // Deliberately not inlined: it is rare, and inlined copies thrash the instruction cache.
   __device__ __noinline__ void offer(float s, int j, int* tab_idx, float* tab_val) {
     if (n_app < (uint32_t)kMaxCand) {
       tab_idx[n_app] = j;
@@ -121,15 +122,18 @@ struct RowTracker {
     } else {
       int worst = 0;
       float wv = tab_val[0];
+      int wj = tab_idx[0];
 #pragma unroll
       for (int q = 1; q < kMaxCand; ++q) {
         const float v = tab_val[q];
-        if (v > wv) {
+        const int jq = tab_idx[q];
+        if (v > wv || (v == wv && jq > wj)) {
           wv = v;
+          wj = jq;
           worst = q;
         }
       }
-      if (s < wv) {
+      if (s < wv || (s == wv && j < wj)) {
         evicted = fminf(evicted, wv);
         tab_idx[worst] = j;
         tab_val[worst] = s;

@@ -244,39 +244,81 @@ def test_epoch_entropy_error():
 
 
 def test_full_size_properties_10m_rows():
-    """Size-independent checks at a BASELINE-sized shard (10M x 256 would take the oracle hours):
-    counts sum to N, sum of per-neuron sk-weighted sums equals the direct column sum, repeatability."""
+    """BASELINE.json config 3 at full size (10M x 256, 64 x 64 map; the oracle would need hours):
+    size-independent properties + oracle parity of a row sub-sample, over three consecutive epochs of the
+    real trajectory (random-row prototypes, then smooth / collapsed maps)."""
     import torch
 
-    n, d, side = 2_000_000, 256, 64
+    n, d, side = 10_000_000, 256, 64
+    m = side * side
     g = torch.Generator(device="cuda").manual_seed(0)
     centers = torch.randn(64, d, device="cuda", generator=g) * 2
-    lab = torch.randint(0, 64, (n,), device="cuda", generator=g)
-    Xd = centers[lab] + torch.randn(n, d, device="cuda", generator=g)
-    X = Xd.cpu().numpy()
-    del Xd
-    W = X[np.random.default_rng(0).choice(n, side * side, replace=False)].astype(np.float64)
+    X = torch.empty((n, d), dtype=torch.float32, device="cuda")
+    for s0 in range(0, n, 1 << 20):
+        s1 = min(n, s0 + (1 << 20))
+        lab = torch.randint(0, 64, (s1 - s0,), device="cuda", generator=g)
+        X[s0:s1] = centers[lab] + torch.randn(s1 - s0, d, device="cuda", generator=g)
     e = engine(bmu_backend="tensor")
-    e.load_data(X, None, 0)
-    e.set_map(W)
+    stats = e.load_device_data(X)
+    assert stats["n_samples"] == n
+    e.init_map_from_rows(np.random.default_rng(0).choice(n, m, replace=False), capacity=m)
     e.set_hops(hop_u16(O.hop_matrix_grid(side, side)))
-    r1 = e.epoch(12.8, True, False)
-    part = e.part[: side * side * d + 3 * side * side].cpu().numpy()
-    m = side * side
-    Sk, sk, cnt, E = part[: m * d].reshape(m, d), part[m * d : m * d + m], r1["counts"], r1["error"]
-    assert cnt.sum() == n and (cnt >= 0).all()
-    # winners of a sub-sample against the oracle
-    sub = np.random.default_rng(1).choice(n, 3000, replace=False)
-    idx = e.idx.view(-1)[:n].cpu().numpy()[sub]
-    assert_bmu_parity(idx.astype(np.int64), X[sub], W)
-    # linearity: sum_j Sk_j = sum_i k_i x_i, checked through sum_j sk_j bounds and E >= 0
-    assert (sk[cnt > 0] > 0).all() and (sk <= cnt + 1e-9).all() and (E >= 0).all()
-    assert np.isfinite(Sk).all()
+    sub = torch.from_numpy(np.sort(np.random.default_rng(1).choice(n, 2000, replace=False))).cuda()
+    Xs = X[sub].cpu().numpy()
+    for epoch, sigma in enumerate((12.8, 12.4, 12.1)):
+        W = e.weights()
+        r = e.epoch(sigma, True, False)
+        part = e.part[: m * d + 3 * m]
+        Sk, sk = part[: m * d].view(m, d), part[m * d : m * d + m]
+        cnt, E = r["counts"], r["error"]
+        # every sample is counted once; weights in (0, 1]; errors are sums of distances
+        assert cnt.sum() == n and (cnt >= 0).all()
+        skh = sk.cpu().numpy()
+        assert (skh[cnt > 0] > 0).all() and (skh <= cnt + 1e-6).all() and (E >= 0).all() and (E[cnt == 0] == 0).all()
+        assert bool(torch.isfinite(Sk).all())
+        # winners of the sub-sample against the float64 oracle (exact outside the 1e-6 near-tie set)
+        idx = e.idx.view(-1)[:n][sub].cpu().numpy().astype(np.int64)
+        n_strict, n_loose = assert_bmu_parity(idx, Xs, W)
+        assert n_strict > 1000
+        # linearity: sum_j E_j = sum_i d_i, checked on the sub-sample's share via exact distances
+        d_sub = np.linalg.norm(Xs.astype(np.float64) - W[idx], axis=1)
+        assert E.sum() / n == pytest.approx(d_sub.mean(), rel=0.05)
+        assert np.isfinite(r["change"]) and r["change"] > 0
+    # repeatability: the same state gives the same counts and (to float64 round-off) the same sums
+    W = e.weights()
     e.set_map(W)
-    r2 = e.epoch(12.8, True, False)
+    r1 = e.epoch(11.0, True, False)
+    e.set_map(W)
+    r2 = e.epoch(11.0, True, False)
     np.testing.assert_array_equal(r1["counts"], r2["counts"])
-    np.testing.assert_allclose(r1["error"], r2["error"], rtol=1e-6)
+    np.testing.assert_allclose(r1["error"], r2["error"], rtol=1e-12)
+    assert r1["change"] == pytest.approx(r2["change"], rel=1e-12)
     e.close()
+
+
+def test_strict_ties_and_worst_case_bound_agree_with_default():
+    """`strict_ties` (flagged samples always re-scored against all prototypes) and bound_scale = 1
+    (Cauchy-Schwarz worst case) must give the oracle's winners too; the default may only differ inside
+    the 1e-6 near-tie set."""
+    n, d, side = 30000, 128, 32
+    X = _datasets.gmm(n, d, 16, 8)
+    rng = np.random.default_rng(3)
+    W_rows = X[rng.choice(n, side * side, replace=False)].astype(np.float64)
+    H = O.neighborhood(O.hop_matrix_grid(side, side), 6.0)
+    W = (H @ W_rows) / H.sum(axis=1)[:, None]  # smooth sheet: many near-ties
+    W[100:140] = W[60]  # and a block of exact duplicates
+    ref_gap = O.relative_gap(X, W)
+    _, ref = O.bmu_expansion(X, W, 1)
+    for kw in (dict(), dict(strict_ties=True), dict(bound_scale=1.0), dict(bmu_backend="tensor1", strict_ties=True)):
+        e = engine(**{"bmu_backend": "tensor", **kw})
+        _, idx = e.bmu(X, W, 1)
+        st = e.bmu_stats_host()
+        e.close()
+        ok = ref_gap >= GAP
+        np.testing.assert_array_equal(idx[ok, 0], ref[ok])
+        assert idx[:, 0].min() >= 0 and not np.isin(idx[:, 0], np.arange(100, 140)).any()  # lowest duplicate wins
+        if kw.get("strict_ties"):
+            assert st["flagged"] == st["full_rescans"]
 
 
 # ------------------------------------------------------------------------------------------ full fits

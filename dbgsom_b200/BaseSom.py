@@ -12,7 +12,7 @@ sigma schedule, thresholds, early stopping, and the fitted NetworkX graph `som_`
 
 from __future__ import annotations
 
-from math import exp, log, pi, sqrt
+from math import exp, log, sqrt
 from typing import Any
 
 import numpy as np
@@ -107,10 +107,10 @@ class BaseSom(BaseEstimator):
     def _check_input_data(self, X, y):
         raise NotImplementedError
 
-    def _label_prototypes(self, winners: np.ndarray, y, engine) -> None:
+    def _label_prototypes(self, y, engine) -> None:
         raise NotImplementedError
 
-    def _fit(self, winners: np.ndarray) -> None:
+    def _fit(self, engine) -> None:
         pass
 
     def predict(self, X):
@@ -226,7 +226,7 @@ class BaseSom(BaseEstimator):
             if self._hops_dirty:
                 # the reference recomputes all-pairs hops every epoch (quirk Q3); they only
                 # change when the map grew
-                engine.set_hops(topo.hop_matrix_u16())
+                engine.set_hops_from_topology(topo)
                 self._hops_dirty = False
             result = engine.epoch(
                 sigma=self._current_sigma(),
@@ -257,10 +257,11 @@ class BaseSom(BaseEstimator):
     def _finalize(self, engine, y) -> None:
         """Everything `fit` does after `_grow_som` (dbgsom/BaseSom.py:116-127).
 
-        The reference runs four to five separate BMU passes here (topographic error,
-        quantisation error, node statistics, classifier labelling, `labels_`); two passes on
-        the device feed all of them (a top-2 pass on the pre-update prototypes, a top-1 pass
-        on the final reduced map).
+        The reference runs four to five separate BMU passes with Python loops over the samples here
+        (topographic error, quantisation error, node statistics, classifier labelling, `labels_`).
+        Two BMU searches on the device feed all of them (a top-2 pass on the pre-update prototypes,
+        a top-1 pass on the final reduced map) and the per-sample reductions run on the device too
+        (`engine.final_statistics`, `engine.label_histogram`); only per-neuron vectors come back.
         """
         topo = self._topology
         # Quirk kept for parity: after the loop the reference's `weights_` / `neurons_` still
@@ -268,36 +269,22 @@ class BaseSom(BaseEstimator):
         # the loop body, dbgsom/BaseSom.py:397-401), so topographic error, quantisation
         # error and node statistics are measured against the prototypes BEFORE the final
         # update, while the graph (and the final `weights_`) carry the updated ones.
-        dist2, idx2 = engine.bmu_train(n_bmu=2, previous=True)
-        m_stats = engine.n_previous_rows
-        winners, dist = idx2[:, 0], dist2[:, 0]
+        st = engine.final_statistics(topo.positions(), topo.degrees())
         n_total = engine.n_samples_global
-
         # topographic error: grid distance of the two BMUs > 1.5 (dbgsom/BaseSom.py:924-953)
-        pos = topo.positions().astype(np.float64)
-        sep = pos[idx2[:, 0]] - pos[idx2[:, 1]]
-        te_count = float(np.count_nonzero(np.sqrt((sep * sep).sum(axis=1)) > 1.5))
-        qe_sum = float(dist.sum())
-        te_count, qe_sum = engine.allreduce_scalars([te_count, qe_sum])
-        self.topographic_error_ = te_count / n_total
-        self.quantization_error_ = qe_sum / n_total
+        self.topographic_error_ = st["te_count"] / n_total
+        self.quantization_error_ = st["qe_sum"] / n_total
 
         # node statistics (dbgsom/BaseSom.py:181-221)
         m = len(topo)
-        if m_stats != m:
+        if st["n_rows"] != m:
             raise RuntimeError(
                 "the map grew in the final epoch (coarse_training_frac >= 1); the reference "
                 "fails in this configuration as well (hit_count missing on the new nodes)"
             )
-        weights = engine.weights()
-        avg_dist = _u_matrix(weights, topo)
-        bandwidth = avg_dist.mean()
-        hits = np.bincount(winners, minlength=m).astype(np.float64)
-        kern = np.exp(-(dist**2) / (2 * bandwidth**2)) / (bandwidth * sqrt(2 * pi))
-        dens_sum = np.bincount(winners, weights=kern, minlength=m)
-        hits, dens_sum = engine.allreduce_arrays([hits, dens_sum])
+        weights, avg_dist, hits = st["weights"], st["avg_dist"], st["hits"]
         with np.errstate(divide="ignore", invalid="ignore"):
-            density = np.where(hits > 0, dens_sum / hits, 0.0)
+            density = np.where(hits > 0, st["dens_sum"] / hits, 0.0)
 
         # neurons without samples leave the map (dbgsom/BaseSom.py:223-235)
         dead = np.flatnonzero(hits == 0)
@@ -317,12 +304,11 @@ class BaseSom(BaseEstimator):
         self._distance_matrix = self._topology.hop_matrix()
 
         # prototype labels and `labels_` use the UPDATED, reduced map (dbgsom/BaseSom.py:121,
-        # :127; SomVQ.py:150-152; SomClassifier.py:130-152): one more BMU pass
+        # :127; SomVQ.py:150-152; SomClassifier.py:130-152): one more BMU pass, kept on the device
         engine.keep_rows(alive)
-        _, idx1 = engine.bmu_train(n_bmu=1)
-        train_winners = idx1[:, 0]
-        self._label_prototypes(train_winners, y, engine)
-        self._fit(train_winners)
+        engine.final_winners()
+        self._label_prototypes(y, engine)
+        self._fit(engine)
 
     # ------------------------------------------------------------------ inference helpers
     def _get_winning_neurons(self, data, n_bmu: int):
@@ -369,25 +355,3 @@ class BaseSom(BaseEstimator):
             transform_algorithm="lasso_lars",
         )
         return coder.transform(normalize(X))
-
-
-def _u_matrix(weights: np.ndarray, topo: MapTopology) -> np.ndarray:
-    """Mean input-space distance of each prototype to ALL adjacency entries of the map.
-
-    The reference averages over the neighbour lists of the whole graph, not over each
-    node's own neighbours (`_get_u_matrix`, dbgsom/BaseSom.py:320-337, quirk Q12), i.e. a
-    degree-weighted mean distance to every prototype.
-    """
-    from scipy.spatial.distance import cdist
-
-    m = len(topo)
-    deg = np.array([len(a) for a in topo.adj], dtype=np.float64)
-    total = deg.sum()
-    if total == 0:
-        return np.full(m, np.nan)
-    out = np.empty(m)
-    step = max(1, int(2**24 // max(m, 1)))
-    for s in range(0, m, step):
-        d = cdist(weights[s : s + step], weights)
-        out[s : s + step] = (d * deg[None, :]).sum(axis=1) / total
-    return out

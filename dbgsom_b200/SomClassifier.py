@@ -25,20 +25,15 @@ class SomClassifier(BaseSom, TransformerMixin, ClassifierMixin):
         X, y = check_X_y(X=X, y=y, ensure_min_samples=4, dtype=[np.float64, np.float32])
         return X, y
 
-    def _label_prototypes(self, winners, y, engine) -> None:
+    def _label_prototypes(self, y, engine) -> None:
         """Majority class and class frequencies per prototype (dbgsom/SomClassifier.py:130-152).
 
         `statistics.mode` returns, among the most frequent classes, the one met first in
         sample order; the per-(prototype, class) first-occurrence index reproduces that.
+        The class histogram and first occurrences are reduced on the device (`dbgsom_label_hist`).
         """
         m, c = len(self.neurons_), len(self.classes_)
-        flat = winners.astype(np.int64) * c + y.astype(np.int64)
-        counts = np.bincount(flat, minlength=m * c).astype(np.float64)
-        first = np.full(m * c, np.iinfo(np.int64).max, dtype=np.int64)
-        order = np.arange(flat.size, dtype=np.int64) + engine.sample_offset
-        np.minimum.at(first, flat, order)
-        (counts,) = engine.allreduce_arrays([counts])
-        (first,) = engine.allreduce_arrays([first], op="min")
+        counts, first = engine.label_histogram(c)
         counts, first = counts.reshape(m, c), first.reshape(m, c)
         for j, node in enumerate(self.neurons_):
             row = counts[j]

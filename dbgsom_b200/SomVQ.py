@@ -24,7 +24,7 @@ class SomVQ(BaseSom, ClusterMixin, TransformerMixin):
         X = check_array(array=X, ensure_min_samples=4, dtype=[np.float64, np.float32])
         return X, None
 
-    def _label_prototypes(self, winners, y, engine) -> None:
+    def _label_prototypes(self, y, engine) -> None:
         # dbgsom/SomVQ.py:126-128 -- label == ordinal of the node
         for i, node in enumerate(self.som_):
             self.som_.nodes[node]["label"] = i
@@ -36,7 +36,7 @@ class SomVQ(BaseSom, ClusterMixin, TransformerMixin):
         _, labels = self._get_winning_neurons(X, n_bmu=1)
         return labels
 
-    def _fit(self, winners) -> None:
+    def _fit(self, engine) -> None:
         # dbgsom/SomVQ.py:150-152: labels_ = predict(X); removed neurons never won a
-        # sample, so the training winners renumbered to the reduced map are that result
-        self.labels_ = np.asarray(winners, dtype=np.int64)
+        # sample, so the training winners on the reduced map are that result
+        self.labels_ = np.asarray(engine.winners_host(), dtype=np.int64)

@@ -13,10 +13,11 @@ _LIB = None
 LIB_NAME = "libdbgsom_b200.so"
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_CAND = 8
 BMU_SIMT = 0
 BMU_TENSOR = 1
+HOPS_MAX_M = 28000
 
 c_void_p, c_int, c_int32, c_int64, c_size_t, c_float, c_double = (
     C.c_void_p, C.c_int, C.c_int32, C.c_int64, C.c_size_t, C.c_float, C.c_double,
@@ -120,6 +121,14 @@ SIGNATURES = {
     "dbgsom_smooth": (c_int, [C.POINTER(SmoothArgs), c_void_p]),
     "dbgsom_apply_row_ops": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "dbgsom_gather_rows": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "dbgsom_node_stats": (
+        c_int, [c_void_p, c_int32, c_void_p, c_int32, c_int64, c_void_p, c_int32, c_double, c_void_p, c_void_p]
+    ),
+    "dbgsom_umatrix": (c_int, [c_void_p, c_int32, c_int32, c_int64, c_void_p, c_void_p, c_void_p]),
+    "dbgsom_label_hist": (
+        c_int, [c_void_p, c_int32, c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p]
+    ),
+    "dbgsom_hops": (c_int, [c_void_p, c_int32, c_void_p, c_int64, c_void_p]),
 }
 
 

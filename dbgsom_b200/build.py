@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libdbgsom_b200.so")
-SOURCES = ["capi.cu", "prep.cu", "bmu_simt.cu", "bmu_tc.cu", "bmu_resolve.cu", "accumulate.cu", "smooth.cu"]
+SOURCES = ["capi.cu", "prep.cu", "bmu_simt.cu", "bmu_tc.cu", "bmu_resolve.cu", "accumulate.cu", "smooth.cu", "post.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "dbgsom_b200.h")]
 
 

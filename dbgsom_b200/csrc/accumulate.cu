@@ -20,6 +20,9 @@
 // by ~1e-7 relative from epoch to epoch and the fit stops at a different epoch (or never).
 // B200 has the float64 rate for this (~3 DFMA per sample element, far below the HBM time).  The M x D table is never privatised in
 // shared memory (4 MB at 4096 x 256); traffic is N*(4D+8) + a few M*D words.
+#include <cstdlib>
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace dbgsom {
@@ -134,28 +137,45 @@ __global__ void __launch_bounds__(SCAT_THREADS) scatter_kernel(const int32_t* __
   }
 }
 
-// ------------------------------------------------------------------------------------------ accumulate
-constexpr int ACC_THREADS = 256;
-constexpr int ACC_STAGES = 2;
-
-__device__ __forceinline__ uint32_t acc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void acc_mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "ACC_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra ACC_DONE;\n"
-      "bra ACC_WAIT;\n"
-      "ACC_DONE:\n"
-      "}\n" ::"r"(acc_smem_u32(bar)),
-      "r"(parity)
-      : "memory");
+// Block-local counting sort for maps of 512 .. 24576 neurons: a CTA takes a chunk of samples, counts
+// its winners in shared memory, reserves one contiguous run per (chunk, winner) with ONE global atomic,
+// then hands out the slots with shared-memory atomics.  The per-sample global atomics of
+// scatter_kernel (10M on 4096 addresses at config 3, 0.53 ms) become <= M per chunk.
+constexpr int SCAT2_THREADS = 1024;
+__global__ void __launch_bounds__(SCAT2_THREADS) scatter_chunk_kernel(const int32_t* __restrict__ bmu, int64_t N, int M,
+                                                                     const int32_t* __restrict__ offsets,
+                                                                     int32_t* __restrict__ cursor,
+                                                                     int32_t* __restrict__ perm, int64_t chunk) {
+  extern __shared__ int32_t sc_smem[];  // [M] local counts / cursors, [M] global base of this chunk's run
+  int32_t* lcount = sc_smem;
+  int32_t* lbase = sc_smem + M;
+  const int64_t c0 = (int64_t)blockIdx.x * chunk;
+  const int64_t c1 = c0 + chunk < N ? c0 + chunk : N;
+  for (int j = threadIdx.x; j < M; j += SCAT2_THREADS) lcount[j] = 0;
+  __syncthreads();
+  for (int64_t i = c0 + threadIdx.x; i < c1; i += SCAT2_THREADS) {
+    const int b = bmu[i];
+    if ((unsigned)b < (unsigned)M) atomicAdd(&lcount[b], 1);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < M; j += SCAT2_THREADS) {
+    const int c = lcount[j];
+    lbase[j] = c ? offsets[j] + atomicAdd(&cursor[j], c) : 0;
+    lcount[j] = 0;
+  }
+  __syncthreads();
+  for (int64_t i = c0 + threadIdx.x; i < c1; i += SCAT2_THREADS) {
+    const int b = bmu[i];
+    if ((unsigned)b < (unsigned)M) perm[lbase[b] + atomicAdd(&lcount[b], 1)] = (int32_t)i;
+  }
 }
+
+// ------------------------------------------------------------------------------------------ accumulate
+__device__ __forceinline__ uint32_t acc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // float -> double without the XU pipe.  ncu showed the first version of this kernel bound by
 // F2F.F64.F32 (sm__inst_executed_pipe_xu at 109 % of peak: ~4 conversions per clock and SM); the
-// same value comes from two integer multiplies and two logic ops on the ALU/FMA pipes: the float's
+// same value comes from four integer operations on the ALU/FMA pipes: the float's
 // exponent/mantissa field shifted right by 3 plus the bias difference (1023 - 127) << 20.  Exact
 // for normal floats; zeros and denormals come out with magnitude < 1.2e-38 instead of exactly
 // themselves, far below anything a float64 sum of the data can resolve; inputs are finite
@@ -172,37 +192,34 @@ __device__ __forceinline__ double f32_as_f64(float f) {
 // Afterwards lane l holds the total of row row_of_lane(l); every row is held by 32 / U lanes.
 template <int U>
 __device__ __forceinline__ int row_of_lane(int lane) {
-  return U == 4 ? ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1) : U == 2 ? (lane >> 4) & 1 : 0;
-}
-template <int U>
-__device__ __forceinline__ double reduce_rows(const double (&v)[U], int lane) {
-  double b;
-  if (U == 4) {
-    const bool h16 = lane & 16, h8 = lane & 8;
-    const double a0 = (h16 ? v[2] : v[0]) + __shfl_xor_sync(kFullMask, h16 ? v[0] : v[2], 16);
-    const double a1 = (h16 ? v[3] : v[1]) + __shfl_xor_sync(kFullMask, h16 ? v[1] : v[3], 16);
-    b = (h8 ? a1 : a0) + __shfl_xor_sync(kFullMask, h8 ? a0 : a1, 8);
-    b += __shfl_xor_sync(kFullMask, b, 4);
-  } else if (U == 2) {
-    const bool h16 = lane & 16;
-    b = (h16 ? v[1] : v[0]) + __shfl_xor_sync(kFullMask, h16 ? v[0] : v[1], 16);
-    b += __shfl_xor_sync(kFullMask, b, 8);
-    b += __shfl_xor_sync(kFullMask, b, 4);
-  } else {
-    b = v[0];
-#pragma unroll
-    for (int o = 16; o > 2; o >>= 1) b += __shfl_xor_sync(kFullMask, b, o);
-  }
-  b += __shfl_xor_sync(kFullMask, b, 2);
-  b += __shfl_xor_sync(kFullMask, b, 1);
-  return b;
+  return lane / (32 / U);
 }
 template <int U>
 __device__ __forceinline__ int lane_of_row(int u) {
-  return U == 4 ? (u >> 1) * 16 + (u & 1) * 8 : U == 2 ? u * 16 : 0;
+  return u * (32 / U);
+}
+template <int U, int OFF>
+__device__ __forceinline__ double reduce_rows_step(const double (&v)[U], int lane) {
+  if constexpr (U == 1) {
+    double b = v[0];
+#pragma unroll
+    for (int o = OFF; o > 0; o >>= 1) b += __shfl_xor_sync(kFullMask, b, o);
+    return b;
+  } else {
+    const bool up = lane & OFF;
+    double a[U / 2];
+#pragma unroll
+    for (int i = 0; i < U / 2; ++i)
+      a[i] = (up ? v[U / 2 + i] : v[i]) + __shfl_xor_sync(kFullMask, up ? v[i] : v[U / 2 + i], OFF);
+    return reduce_rows_step<U / 2, OFF / 2>(a, lane);
+  }
+}
+template <int U>
+__device__ __forceinline__ double reduce_rows(const double (&v)[U], int lane) {
+  return reduce_rows_step<U, 16>(v, lane);
 }
 
-// Position of a team in the sorted sample sequence: next position, its segment, the segment's end.
+// Position of a warp in the sorted sample sequence: next position, its segment, the segment's end.
 struct SegCursor {
   int32_t p, seg, seg_end;
   // rows of the next batch: at most U, never across a segment boundary or the end of the range
@@ -217,23 +234,32 @@ struct SegCursor {
 };
 
 // VPL : float4 per lane per row slab;  WPR : warps cooperating on one row (team size);
-// U   : rows per batch (their sample weights are evaluated together, lane u doing row u, so the
-//       float64 exp/sqrt costs 1/U per row).
-// Every team owns one contiguous range of the sorted sequence.  Rows travel HBM -> shared memory by
-// 1-D bulk async copies (cp.async.bulk, one instruction per row, completion on an mbarrier) into a
-// ring of ACC_STAGES batches per team, so the copies of the next batches are in flight while the
-// current one is reduced and no registers are tied up by loads.  A team handles columns
-// [tw * 128 * VPL, (tw + 1) * 128 * VPL) of each row with warp tw.
+// U   : rows per batch (their sample weights are evaluated together, lane group u doing row u, so
+//       the float64 exp/sqrt costs 1/U per row);  STAGES : depth of the copy ring.
+// Every team owns one contiguous range of the sorted sequence; warp tw of a team handles columns
+// [tw * 128 * VPL, (tw + 1) * 128 * VPL) of each row, and every LANE stages exactly the 16-byte
+// pieces it consumes itself: HBM -> shared memory with cp.async (LDGSTS, L2 only), one commit group
+// per batch, STAGES - 1 batches in flight per warp.  Shared memory is therefore a private staging
+// area per lane -- no barrier, fence or elected issuer is involved and no registers are tied up by
+// loads in flight.  (The second version used one bulk copy per row issued by an elected lane:
+// ~30 instructions per copy on the uniform datapath, 18 % of the kernel's instruction stream.)
+// Each element is converted to float64 ONCE and stays in registers (U * VPL * 4 doubles per lane) for
+// both uses -- the distance and, once the row's weight is known, the k * x sum: the first version
+// converted twice and was issue bound on the conversions (ncu: 69 % of the issue slots, 42 % of
+// DRAM peak).  The permutation entries of the next 64 positions are prefetched warp-wide.
 // All arithmetic is float64: distances by direct differences, k = 1 - sqrt(1 - exp(-d^2 / V))
 // literally as dbgsom/BaseSom.py:536-537, sums in float64 registers.
-template <int VPL, int WPR, int U>
-__global__ void __launch_bounds__(ACC_THREADS) accumulate_kernel(
+template <int VPL, int WPR, int U, int THREADS, int STAGES, bool FULLD>
+__global__ void __launch_bounds__(THREADS, 2) accumulate_kernel(
     const float* __restrict__ X, int64_t N, int D, int64_t ldx, const int32_t* __restrict__ perm,
     const int32_t* __restrict__ offsets, const double* __restrict__ W, int M, double inv_var,
     double* __restrict__ part) {
-  constexpr int TEAMS = ACC_THREADS / 32 / WPR;
-  extern __shared__ __align__(16) float rows_smem[];  // [TEAMS][ACC_STAGES][U][D]
-  __shared__ __align__(8) uint64_t full_bar[TEAMS][ACC_STAGES];
+  constexpr int TEAMS = THREADS / 32 / WPR;
+  constexpr int SLOT_BYTES = U * VPL * 512;          // one batch of one warp
+  constexpr int WARP_BYTES = STAGES * SLOT_BYTES + VPL * 1024;
+  // per warp: [STAGES][U][VPL][32 lanes x 16 B] staged samples, then [VPL][32 lanes x 32 B] the current
+  // segment's float64 prototype (each lane keeps the 4 columns it owns; in registers it cost 16 of them)
+  extern __shared__ __align__(16) uint8_t stage_smem[];
   __shared__ double red[TEAMS][2][WPR][U];  // cross-warp partial squared distances (double buffered)
 
   const int lane = threadIdx.x & 31;
@@ -242,20 +268,11 @@ __global__ void __launch_bounds__(ACC_THREADS) accumulate_kernel(
   const int tw = warp % WPR;
   const int col0 = tw * 128 * VPL + lane * 4;
   const int32_t total = offsets[M];  // samples that have a winner (== N without NaN rows)
-  const bool issuer = tw == 0 && lane == 0;
-  float* ring = rows_smem + (size_t)team * ACC_STAGES * U * D;
-  const uint32_t row_bytes = (uint32_t)D * 4u;
-
-  if (issuer) {
-    for (int s = 0; s < ACC_STAGES; ++s)
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(acc_smem_u32(&full_bar[team][s])));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  double* __restrict__ Sk = part;
-  double* __restrict__ sk = part + (int64_t)M * D;
-  double* __restrict__ En = sk + 2 * (int64_t)M;
+  const uint32_t my_smem = acc_smem_u32(stage_smem) + (uint32_t)warp * WARP_BYTES + lane * 16;
+  const uint32_t my_w = acc_smem_u32(stage_smem) + (uint32_t)warp * WARP_BYTES + STAGES * SLOT_BYTES + lane * 32;
+  bool act[VPL];  // FULLD: D == 128 * VPL * WPR, every slab of every lane is inside the row
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) act[v] = FULLD || col0 + v * 128 < D;
 
   const int64_t n_teams = (int64_t)gridDim.x * TEAMS;
   const int64_t team_id = (int64_t)blockIdx.x * TEAMS + team;
@@ -270,45 +287,60 @@ __global__ void __launch_bounds__(ACC_THREADS) accumulate_kernel(
     if (offsets[mid] <= p_begin) lo = mid; else hi = mid;
   }
   SegCursor use{p_begin, lo, offsets[lo + 1]};  // consumer position
-  SegCursor pre = use;                          // prefetch position (runs ACC_STAGES - 1 batches ahead)
+  SegCursor pre = use;                          // prefetch position (runs STAGES - 1 batches ahead)
 
-  auto issue = [&](int stage) {  // all lanes advance the cursor, one lane issues the copies
-    if (pre.p >= p_end) return;
-    const int nb = pre.next_batch(offsets, p_end, U);
-    if (issuer) {
-      uint64_t* bar = &full_bar[team][stage];
-      // order the team's earlier generic-proxy reads of this slot before the async-proxy writes
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(acc_smem_u32(bar)), "r"(nb * row_bytes)
-                   : "memory");
-      for (int u = 0; u < nb; ++u) {
-        const float* src = X + (int64_t)perm[pre.p + u] * ldx;
-        asm volatile(
-            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                acc_smem_u32(ring + ((size_t)stage * U + u) * D)),
-            "l"(src), "r"(row_bytes), "r"(acc_smem_u32(bar))
-            : "memory");
+  // permutation window: lane l holds perm[win + l] (cur) and perm[win + 32 + l] (nxt)
+  int32_t win = p_begin;
+  auto perm_at = [&](int32_t p) { return perm[p < total ? p : total - 1]; };
+  int32_t perm_cur = perm_at(win + lane), perm_nxt = perm_at(win + 32 + lane);
+
+  const float* __restrict__ my_src = X + col0;
+  const uint32_t ld32 = (uint32_t)ldx;  // one 32 x 32 -> 64 bit multiply per row address
+  auto issue = [&](int stage) {  // every lane copies its own 16-byte pieces of the next batch
+    if (pre.p < p_end) {
+      const int nb = pre.next_batch(offsets, p_end, U);
+      if (pre.p + nb > win + 64) {  // slide the window (nb <= 32, so one step is enough)
+        win += 32;
+        perm_cur = perm_nxt;
+        perm_nxt = perm_at(win + 32 + lane);
       }
+      const uint32_t dst = my_smem + (uint32_t)stage * SLOT_BYTES;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int o = pre.p + u - win;  // 0 .. 63
+        const int32_t a = __shfl_sync(kFullMask, perm_cur, o & 31);
+        const int32_t b = __shfl_sync(kFullMask, perm_nxt, o & 31);
+        const float* src = my_src + (uint64_t)(uint32_t)(o < 32 ? a : b) * ld32;
+        if (u < nb) {
+#pragma unroll
+          for (int v = 0; v < VPL; ++v)
+            if (FULLD || act[v])
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (u * VPL + v) * 512),
+                           "l"(src + v * 128)
+                           : "memory");
+        }
+      }
+      pre.p += nb;
     }
-    pre.p += nb;
+    asm volatile("cp.async.commit_group;" ::: "memory");  // possibly empty: keeps the group count uniform
   };
 #pragma unroll
-  for (int s = 0; s < ACC_STAGES - 1; ++s) issue(s);
+  for (int s = 0; s < STAGES - 1; ++s) issue(s);
 
-  double w[VPL][4], acc[VPL][4];
-  double run_k = 0.0, run_d = 0.0;
+  double* __restrict__ Sk = part;
+  double acc[VPL][4];
+  double run_k = 0.0, run_d = 0.0;  // sums of the rows this lane evaluates (row slot row_of_lane)
   int seg = -1;
   auto load_w = [&](int sgm) {
     seg = sgm;
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
       const int c = col0 + v * 128;
-      if (c < D) {
+      if (act[v]) {
         const double2 a = *reinterpret_cast<const double2*>(W + (int64_t)seg * D + c);
         const double2 b = *reinterpret_cast<const double2*>(W + (int64_t)seg * D + c + 2);
-        w[v][0] = a.x; w[v][1] = a.y; w[v][2] = b.x; w[v][3] = b.y;
-      } else {
-        w[v][0] = w[v][1] = w[v][2] = w[v][3] = 0.0;
+        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(my_w + v * 1024), "d"(a.x), "d"(a.y) : "memory");
+        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(my_w + v * 1024 + 16), "d"(b.x), "d"(b.y) : "memory");
       }
       acc[v][0] = acc[v][1] = acc[v][2] = acc[v][3] = 0.0;
     }
@@ -319,7 +351,7 @@ __global__ void __launch_bounds__(ACC_THREADS) accumulate_kernel(
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
       const int c = col0 + v * 128;
-      if (c < D) {
+      if (act[v]) {
         double* dst = Sk + (int64_t)seg * D + c;
         atomicAdd(dst + 0, acc[v][0]);
         atomicAdd(dst + 1, acc[v][1]);
@@ -327,109 +359,132 @@ __global__ void __launch_bounds__(ACC_THREADS) accumulate_kernel(
         atomicAdd(dst + 3, acc[v][3]);
       }
     }
+    // every row slot is evaluated by 32 / U lanes with identical results: count each slot once
+    const bool slot_leader = (lane % (32 / U)) == 0;
+    const double tk = warp_sum(slot_leader ? run_k : 0.0);
+    const double td = warp_sum(slot_leader ? run_d : 0.0);
     if (tw == 0 && lane == 0) {
-      atomicAdd(sk + seg, run_k);
-      atomicAdd(En + seg, run_d);
+      atomicAdd(part + (int64_t)M * D + seg, tk);              // sk
+      atomicAdd(part + (int64_t)M * D + 2 * (int64_t)M + seg, td);  // E
     }
   };
 
   int stage = 0, parity = 0;
-  uint32_t phase = 0;
   while (use.p < p_end) {
     const int nb = use.next_batch(offsets, p_end, U);
     if (use.seg != seg) {
       if (seg >= 0) flush();
       load_w(use.seg);
     }
-    issue((stage + ACC_STAGES - 1) % ACC_STAGES);  // refill the slot consumed in the previous iteration
-    acc_mbar_wait(&full_bar[team][stage], phase);
-    const float* rows = ring + (size_t)stage * U * D;
+    issue(stage == 0 ? STAGES - 1 : stage - 1);  // refill the slot consumed in the previous iteration
+    asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 1) : "memory");
+    const uint32_t rows = my_smem + (uint32_t)stage * SLOT_BYTES;
 
-    double part_d2[U];
+    // ALL: the batch has all U rows (the common case) -> no per-row predicates in the unrolled code
+    auto body = [&](auto all_tag) {
+      constexpr bool ALL = decltype(all_tag)::value;
+      double xd[U][VPL][4];
+      double part_d2[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      double t = 0.0;
-      if (u < nb) {
+      for (int u = 0; u < U; ++u) part_d2[u] = 0.0;
 #pragma unroll
-        for (int v = 0; v < VPL; ++v) {
-          const int c = col0 + v * 128;
-          if (c < D) {
-            const float4 x = *reinterpret_cast<const float4*>(rows + u * D + c);
-            // one conversion in four goes through the XU pipe (F2F, ~27 clk per warp instruction, otherwise
-            // idle), the rest through the ALU/FMA pipes: neither saturates
-            const double a = (double)x.x - w[v][0], b = f32_as_f64(x.y) - w[v][1];
-            const double cc = f32_as_f64(x.z) - w[v][2], e = f32_as_f64(x.w) - w[v][3];
-            t = fma(a, a, t);
-            t = fma(b, b, t);
-            t = fma(cc, cc, t);
-            t = fma(e, e, t);
+      for (int v = 0; v < VPL; ++v) {
+        if (FULLD || act[v]) {
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (ALL || u < nb) {
+              float4 x;
+              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                           : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
+                           : "r"(rows + (u * VPL + v) * 512));
+              // one conversion in four goes through the XU pipe (F2F, ~27 clk per warp instruction, otherwise
+              // idle), the rest through the ALU/FMA pipes: neither saturates
+              xd[u][v][0] = (double)x.x;
+              xd[u][v][1] = f32_as_f64(x.y);
+              xd[u][v][2] = f32_as_f64(x.z);
+              xd[u][v][3] = f32_as_f64(x.w);
+            }
+          }
+          // the prototype's columns are read once per batch and used for all its rows
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            double w0, w1;
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(w0), "=d"(w1) : "r"(my_w + v * 1024 + h * 16));
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              if (ALL || u < nb) {
+                const double a = xd[u][v][2 * h] - w0;
+                part_d2[u] = fma(a, a, part_d2[u]);
+                const double b = xd[u][v][2 * h + 1] - w1;
+                part_d2[u] = fma(b, b, part_d2[u]);
+              }
+            }
           }
         }
       }
-      part_d2[u] = t;
-    }
-    double my_d2 = reduce_rows<U>(part_d2, lane);  // lane l: squared distance of row row_of_lane(l)
-    if (WPR > 1) {
+      double my_d2 = reduce_rows<U>(part_d2, lane);  // lane l: squared distance of row row_of_lane(l)
+      if (WPR > 1) {
 #pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (lane == lane_of_row<U>(u)) red[team][parity][tw][u] = my_d2;
-      asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(WPR * 32));
-      my_d2 = 0.0;
+        for (int u = 0; u < U; ++u)
+          if (lane == lane_of_row<U>(u)) red[team][parity][tw][u] = my_d2;
+        asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(WPR * 32));
+        my_d2 = 0.0;
 #pragma unroll
-      for (int q = 0; q < WPR; ++q) my_d2 += red[team][parity][q][row_of_lane<U>(lane)];
-      parity ^= 1;
-    }
-    // each lane evaluates the weight and the distance of its row (32 / U lanes per row, redundantly)
-    const double my_dist = sqrt(my_d2);
-    const double my_k = 1.0 - sqrt(1.0 - exp(-inv_var * (my_dist * my_dist)));
+        for (int q = 0; q < WPR; ++q) my_d2 += red[team][parity][q][row_of_lane<U>(lane)];
+        parity ^= 1;
+      }
+      // each lane evaluates the weight and the distance of its row slot (32 / U lanes per slot, redundantly)
+      const double my_dist = sqrt(my_d2);
+      const double my_k = 1.0 - sqrt(1.0 - exp(-inv_var * (my_dist * my_dist)));
+      if (ALL || row_of_lane<U>(lane) < nb) {
+        run_k += my_k;
+        run_d += my_dist;
+      }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (u < nb) {
+      for (int u = 0; u < U; ++u) {
         const double k = __shfl_sync(kFullMask, my_k, lane_of_row<U>(u));
-        run_k += k;
-        run_d += __shfl_sync(kFullMask, my_dist, lane_of_row<U>(u));
+        if (ALL || u < nb) {
 #pragma unroll
-        for (int v = 0; v < VPL; ++v) {
-          const int c = col0 + v * 128;
-          if (c < D) {
-            const float4 x = *reinterpret_cast<const float4*>(rows + u * D + c);
-            acc[v][0] = fma(k, f32_as_f64(x.x), acc[v][0]);
-            acc[v][1] = fma(k, f32_as_f64(x.y), acc[v][1]);
-            acc[v][2] = fma(k, f32_as_f64(x.z), acc[v][2]);
-            acc[v][3] = fma(k, f32_as_f64(x.w), acc[v][3]);
+          for (int v = 0; v < VPL; ++v) {
+            if (FULLD || act[v]) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) acc[v][q] = fma(k, xd[u][v][q], acc[v][q]);
+            }
           }
         }
       }
-    }
-    use.p += nb;
-    // the slot may be overwritten by the next issue(): every lane of the team is done reading it
-    if (WPR > 1)
-      asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(WPR * 32));
+    };
+    if (nb == U)
+      body(std::true_type{});
     else
-      __syncwarp();
-    if (++stage == ACC_STAGES) {
-      stage = 0;
-      phase ^= 1;
-    }
+      body(std::false_type{});
+    use.p += nb;
+    if (++stage == STAGES) stage = 0;
   }
   if (seg >= 0) flush();
 }
 
 template <int VPL, int WPR, int U>
 int launch_accumulate(const dbgsom_accumulate_args& a, const int32_t* perm, const int32_t* offsets, cudaStream_t s) {
-  constexpr int TEAMS = ACC_THREADS / 32 / WPR;
-  const size_t smem = (size_t)TEAMS * ACC_STAGES * U * a.D * sizeof(float);
-  auto kern = accumulate_kernel<VPL, WPR, U>;
+  // one warp per row (WPR = 1): 6 warps per CTA leave 168 registers per thread at two CTAs per SM, enough
+  // for the U * VPL * 4 converted elements + prototype + sums without spilling (at 128 registers the
+  // loop-carried cursors spilled and every iteration stalled on local-memory loads); teams need 8 warps
+  constexpr int THREADS = WPR == 1 ? 192 : 256;
+  constexpr int STAGES = WPR == 1 ? 4 : 3;
+  constexpr int TEAMS = THREADS / 32 / WPR;
+  const size_t smem = (size_t)(THREADS / 32) * (STAGES * U * VPL * 512 + VPL * 1024);
+  auto kern = a.D == 128 * VPL * WPR ? accumulate_kernel<VPL, WPR, U, THREADS, STAGES, true>
+                                     : accumulate_kernel<VPL, WPR, U, THREADS, STAGES, false>;
   DBGSOM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = (int)((220 * 1024) / (smem + 2048));
-  if (per_sm > 4) per_sm = 4;
+  if (per_sm > 2) per_sm = 2;  // register budget
   if (per_sm < 1) per_sm = 1;
   int64_t blocks = 148 * per_sm;
   const int64_t useful = ceil_div<int64_t>(ceil_div<int64_t>(a.N, 4 * U), TEAMS);  // >= 4 batches per team
   if (blocks > useful) blocks = useful;
   if (blocks < 1) blocks = 1;
-  kern<<<(unsigned)blocks, ACC_THREADS, smem, s>>>(a.d_X, a.N, a.D, a.ldx, perm, offsets, a.d_W, a.M,
-                                                  a.inv_total_variance, a.d_part);
+  kern<<<(unsigned)blocks, THREADS, smem, s>>>(a.d_X, a.N, a.D, a.ldx, perm, offsets, a.d_W, a.M,
+                                              a.inv_total_variance, a.d_part);
   DBGSOM_LAUNCH_CHECK();
   return DBGSOM_OK;
 }
@@ -479,15 +534,33 @@ int run_accumulate(const dbgsom_accumulate_args& a, cudaStream_t s) {
   }
   scan_kernel<<<1, SCAN_THREADS, 0, s>>>(ws.counts, a.M, ws.offsets, ws.cursor, a.d_part + M * D + M);
   DBGSOM_LAUNCH_CHECK();
-  {
+  if (a.M >= 512 && a.M <= 24576 && a.N >= (1 << 18)) {
+    const size_t smem = (size_t)a.M * 8;
+    DBGSOM_CUDA_TRY(cudaFuncSetAttribute(scatter_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // one wave: two resident CTAs per SM (one when the tables need more than half the shared memory)
+    const int64_t slots = 148 * (smem <= 100 * 1024 ? 2 : 1);
+    int64_t chunk = round_up<int64_t>(ceil_div<int64_t>(a.N, slots), SCAT2_THREADS);
+    if (chunk < 16384) chunk = 16384;
+    scatter_chunk_kernel<<<(unsigned)ceil_div<int64_t>(a.N, chunk), SCAT2_THREADS, smem, s>>>(
+        a.d_bmu, a.N, a.M, ws.offsets, ws.cursor, ws.perm, chunk);
+    DBGSOM_LAUNCH_CHECK();
+  } else {
     int64_t blocks = ceil_div<int64_t>(a.N, SCAT_THREADS * 4);
     if (blocks > 148 * 16) blocks = 148 * 16;
     scatter_kernel<<<(unsigned)blocks, SCAT_THREADS, 0, s>>>(a.d_bmu, a.N, a.M, ws.offsets, ws.cursor, ws.perm);
     DBGSOM_LAUNCH_CHECK();
   }
   const int D4 = a.D;
-  if (D4 <= 128) return launch_accumulate<1, 1, 4>(a, ws.perm, ws.offsets, s);
-  if (D4 <= 256) return launch_accumulate<2, 1, 4>(a, ws.perm, ws.offsets, s);
+  static const char* tune_u = getenv("DBGSOM_ACC_ROWS");  // tuning switch: rows per batch for D <= 256
+  const int u_small = tune_u ? atoi(tune_u) : 0;
+  if (D4 <= 128) {
+    if (u_small == 4) return launch_accumulate<1, 1, 4>(a, ws.perm, ws.offsets, s);
+    return launch_accumulate<1, 1, 8>(a, ws.perm, ws.offsets, s);
+  }
+  if (D4 <= 256) {
+    if (u_small == 2) return launch_accumulate<2, 1, 2>(a, ws.perm, ws.offsets, s);
+    return launch_accumulate<2, 1, 4>(a, ws.perm, ws.offsets, s);
+  }
   if (D4 <= 512) return launch_accumulate<4, 1, 2>(a, ws.perm, ws.offsets, s);
   if (D4 <= 1024) return launch_accumulate<4, 2, 2>(a, ws.perm, ws.offsets, s);
   if (D4 <= 2048) return launch_accumulate<4, 4, 2>(a, ws.perm, ws.offsets, s);

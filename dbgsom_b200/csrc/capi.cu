@@ -13,6 +13,10 @@ size_t accumulate_workspace_bytes(int64_t, int);
 int run_accumulate(const dbgsom_accumulate_args&, cudaStream_t);
 size_t smooth_workspace_bytes(int, int);
 int run_smooth(const dbgsom_smooth_args&, cudaStream_t);
+int run_node_stats(const int32_t*, int, const double*, int, int64_t, const int32_t*, int, double, double*, cudaStream_t);
+int run_label_hist(const int32_t*, int, const int32_t*, int64_t, int64_t, int, int, int32_t*, int64_t*, cudaStream_t);
+int run_umatrix(const double*, int, int, int64_t, const double*, double*, cudaStream_t);
+int run_hops(const int32_t*, int, uint16_t*, int64_t, cudaStream_t);
 }  // namespace dbgsom
 
 using namespace dbgsom;
@@ -140,6 +144,35 @@ int dbgsom_gather_rows(const float* d_X, int64_t ldx, int D, const int64_t* d_ro
                        void* stream) {
   if (!d_X || !d_rows || !d_W || D <= 0 || n_rows < 0 || ldx < D) return DBGSOM_E_BADARG;
   return run_gather_rows(d_X, ldx, D, d_rows, n_rows, d_W, as_stream(stream));
+}
+
+int dbgsom_node_stats(const int32_t* d_idx, int32_t idx_stride, const double* d_dist, int32_t dist_stride, int64_t N,
+                      const int32_t* d_pos, int32_t M, double bandwidth, double* d_out, void* stream) {
+  if (!d_idx || !d_dist || !d_pos || !d_out || N <= 0 || M <= 0 || idx_stride < 1 || dist_stride < 1)
+    return DBGSOM_E_BADARG;
+  if (!(bandwidth > 0.0)) return DBGSOM_E_BADARG;
+  return run_node_stats(d_idx, idx_stride, d_dist, dist_stride, N, d_pos, M, bandwidth, d_out, as_stream(stream));
+}
+
+int dbgsom_umatrix(const double* d_W, int32_t M, int32_t D, int64_t ldw, const double* d_colw, double* d_out,
+                   void* stream) {
+  if (!d_W || !d_colw || !d_out || M <= 0 || D <= 0 || ldw < D) return DBGSOM_E_BADARG;
+  return run_umatrix(d_W, M, D, ldw, d_colw, d_out, as_stream(stream));
+}
+
+int dbgsom_label_hist(const int32_t* d_idx, int32_t idx_stride, const int32_t* d_labels, int64_t N,
+                      int64_t sample_offset, int32_t M, int32_t n_classes, int32_t* d_counts, int64_t* d_first,
+                      void* stream) {
+  if (!d_idx || !d_labels || !d_counts || !d_first || N <= 0 || M <= 0 || n_classes <= 0 || idx_stride < 1)
+    return DBGSOM_E_BADARG;
+  return run_label_hist(d_idx, idx_stride, d_labels, N, sample_offset, M, n_classes, d_counts, d_first,
+                        as_stream(stream));
+}
+
+int dbgsom_hops(const int32_t* d_adj, int32_t M, uint16_t* d_hop, int64_t ldh, void* stream) {
+  if (!d_adj || !d_hop || M <= 0 || ldh < M) return DBGSOM_E_BADARG;
+  if (!aligned16(d_adj)) return DBGSOM_E_UNSUPPORTED;
+  return run_hops(d_adj, M, d_hop, ldh, as_stream(stream));
 }
 
 }  // extern "C"

@@ -157,7 +157,8 @@ class DeviceEngine:
 
     def close(self) -> None:
         self._ws.clear()
-        for name in ("X", "X16_hi", "X16_lo", "xnorm16", "W", "W32", "W16_hi", "W16_lo", "labels", "part", "hop"):
+        for name in ("X", "X16_hi", "X16_lo", "xnorm16", "W", "W32", "W16_hi", "W16_lo", "labels", "part", "hop",
+                     "_final_idx"):
             if hasattr(self, name):
                 setattr(self, name, None)
 
@@ -314,6 +315,29 @@ class DeviceEngine:
         # uint16 travels as int16 bit patterns (torch has no uint16 arithmetic; none is needed)
         self.hop = torch.from_numpy(np.ascontiguousarray(hop_u16).view(np.int16)).to(self.dev)
         self.ldh = m
+
+    def set_hops_from_topology(self, topo) -> None:
+        """All-pairs hop counts of the map graph, computed on the device (one BFS per source node,
+        `dbgsom_hops`) from the adjacency table; only maps beyond the kernel's shared-memory limit
+        take the host BFS of `MapTopology.hop_matrix_u16`.  Replaces the per-epoch
+        `nx.floyd_warshall_numpy` of dbgsom/BaseSom.py:401."""
+        torch = self.torch
+        m = len(topo)
+        if m > nat.HOPS_MAX_M:
+            self.set_hops(topo.hop_matrix_u16())
+            return
+        with torch.cuda.device(self.dev):
+            d_adj = torch.from_numpy(topo.adjacency_table()).to(self.dev)
+            self.hop = torch.empty((m, m), dtype=torch.int16, device=self.dev)
+            nat.check(self.lib.dbgsom_hops(d_adj.data_ptr(), m, self.hop.data_ptr(), m, self._stream()), "dbgsom_hops")
+            self.launches += 1
+            self.ldh = m
+            # 0xFFFF (unreachable) reads as -1 in the int16 view, so the maximum is the largest finite hop count
+            self.hop_max = max(int(self.hop.max().item()), 0)
+
+    def hops_host(self) -> np.ndarray:
+        """The device hop matrix as uint16 on the host (tests)."""
+        return self.hop.cpu().numpy().view(np.uint16)
 
     def apply_row_ops(self, ops, n_rows: int) -> None:
         """Prototype rows of the neurons a growth step inserted (see topology.RowOp)."""
@@ -567,6 +591,94 @@ class DeviceEngine:
             dist = torch.empty((self.N, n_bmu), dtype=torch.float64, device=self.dev)
             self._run_bmu(self.X, self.N, self.ldx, x16, W, m, n_bmu, True, idx, dist, backend=be)
             return dist.cpu().numpy(), idx.cpu().numpy().astype(np.int64)
+
+    # ------------------------------------------------------------------ post-training passes
+    def _bmu_train_device(self, n_bmu: int, previous: bool):
+        """Like `bmu_train`, results stay in HBM: (idx int32 [N, n_bmu], dist float64 [N, n_bmu], m)."""
+        torch = self.torch
+        W = self.W[self.cur ^ 1] if previous else self.W[self.cur]
+        m = self.n_previous_rows if previous else self.M
+        n_bmu = min(n_bmu, m)
+        be = self._pick_backend(self.N, m)
+        x16 = None
+        if be[0] == nat.BMU_TENSOR:
+            self._ensure_x16(be[1] == 3)
+            x16 = (self.X16_hi, self.X16_lo, self.xnorm16)
+        idx = torch.empty((self.N, n_bmu), dtype=torch.int32, device=self.dev)
+        dist = torch.empty((self.N, n_bmu), dtype=torch.float64, device=self.dev)
+        self._run_bmu(self.X, self.N, self.ldx, x16, W, m, n_bmu, True, idx, dist, backend=be)
+        return idx, dist, m
+
+    def final_statistics(self, positions: np.ndarray, degrees: np.ndarray) -> dict:
+        """Everything `fit` measures after the loop, reduced on the device (and over ranks):
+        one top-2 BMU search on the PRE-update prototypes (dbgsom/BaseSom.py:116-119 see the
+        stale `weights_`) feeds the topographic error (:924-953), the quantisation error (:904-922)
+        and the node statistics (:181-211); the u-matrix (:320-337) uses the updated prototypes."""
+        torch = self.torch
+        with torch.cuda.device(self.dev):
+            idx, dist, m = self._bmu_train_device(2, previous=True)
+            n_bmu = int(idx.shape[1])
+            M, cur = self.M, self.W[self.cur]
+            total = float(np.sum(degrees))
+            if total > 0:
+                colw = torch.from_numpy(np.ascontiguousarray(degrees, dtype=np.float64) / total).to(self.dev)
+                avg = torch.empty(M, dtype=torch.float64, device=self.dev)
+                nat.check(
+                    self.lib.dbgsom_umatrix(cur.data_ptr(), M, self.ldx, self.ldx, colw.data_ptr(), avg.data_ptr(), self._stream()),
+                    "dbgsom_umatrix",
+                )
+                self.launches += 2
+                avg_host = avg.cpu().numpy()
+            else:
+                avg_host = np.full(M, np.nan)
+            bandwidth = float(avg_host.mean())
+            pos = torch.from_numpy(np.ascontiguousarray(positions[:m], dtype=np.int32)).to(self.dev)
+            out = torch.empty(2 + 2 * m, dtype=torch.float64, device=self.dev)
+            ok = bandwidth > 0 and math.isfinite(bandwidth)
+            nat.check(
+                self.lib.dbgsom_node_stats(
+                    idx.data_ptr(), n_bmu, dist.data_ptr(), n_bmu, self.N, pos.data_ptr(), m,
+                    bandwidth if ok else 1.0, out.data_ptr(), self._stream(),
+                ),
+                "dbgsom_node_stats",
+            )
+            self.launches += 2
+            self.comm.allreduce_(out)
+            o = out.cpu().numpy()
+            dens = o[2 + m :].copy()
+            if not ok:
+                dens[:] = np.nan
+            return {"te_count": float(o[0]), "qe_sum": float(o[1]), "hits": o[2 : 2 + m].copy(), "dens_sum": dens,
+                    "avg_dist": avg_host, "weights": self.weights(), "n_rows": m}
+
+    def final_winners(self) -> None:
+        """Top-1 BMU of the training samples on the current (reduced) map; stays on the device."""
+        with self.torch.cuda.device(self.dev):
+            self._final_idx, _, _ = self._bmu_train_device(1, previous=False)
+
+    def winners_host(self) -> np.ndarray:
+        return self._final_idx[:, 0].cpu().numpy().astype(np.int64)
+
+    def label_histogram(self, n_classes: int):
+        """Class counts [M, C] and first global sample index [M, C] of every (winner, class) cell of the
+        last `final_winners` search, reduced over ranks (dbgsom/SomClassifier.py:130-152)."""
+        torch = self.torch
+        with torch.cuda.device(self.dev):
+            m = self.M
+            counts = torch.empty((m, n_classes), dtype=torch.int32, device=self.dev)
+            first = torch.empty((m, n_classes), dtype=torch.int64, device=self.dev)
+            nat.check(
+                self.lib.dbgsom_label_hist(
+                    self._final_idx.data_ptr(), int(self._final_idx.shape[1]), self.labels.data_ptr(), self.N,
+                    self.sample_offset, m, n_classes, counts.data_ptr(), first.data_ptr(), self._stream(),
+                ),
+                "dbgsom_label_hist",
+            )
+            self.launches += 3
+            counts = counts.to(torch.int64)
+            self.comm.allreduce_(counts)
+            self.comm.allreduce_(first, "min")
+            return counts.cpu().numpy().astype(np.float64), first.cpu().numpy()
 
     def bmu(self, X: np.ndarray, W: np.ndarray, n_bmu: int):
         """Stand-alone BMU search (predict path): host samples against host prototypes."""

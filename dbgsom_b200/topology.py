@@ -260,6 +260,17 @@ class MapTopology:
     def positions(self) -> np.ndarray:
         return np.asarray(self.pos, dtype=np.int64).reshape(-1, 2)
 
+    def adjacency_table(self) -> np.ndarray:
+        """int32 [M, 4]: neighbour indices per node (edge-insertion order), -1 = free slot.
+        Input of the device hop-matrix kernel (`dbgsom_hops`)."""
+        out = np.full((len(self.pos), 4), -1, dtype=np.int32)
+        for i, nbrs in enumerate(self.adj):
+            out[i, : len(nbrs)] = nbrs
+        return out
+
+    def degrees(self) -> np.ndarray:
+        return np.array([len(a) for a in self.adj], dtype=np.float64)
+
     def to_networkx(self, node_attrs: dict[str, list] | None = None):
         """Export as the `som_` graph: same node order and the same adjacency order."""
         import networkx as nx

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define DBGSOM_ABI_VERSION 1
+#define DBGSOM_ABI_VERSION 2
 
 #define DBGSOM_OK 0
 #define DBGSOM_E_BADARG (-1)      /* null pointer, non-positive size, bad enum             */
@@ -249,6 +249,47 @@ int dbgsom_apply_row_ops(double* d_W, int D, const int32_t* d_ops, int n_ops, vo
 /* W[r,:] = X[rows[r],:] (float32 -> float64) -- the start prototypes, dbgsom/BaseSom.py:423-430 */
 int dbgsom_gather_rows(const float* d_X, int64_t ldx, int D, const int64_t* d_rows, int n_rows,
                        double* d_W, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * post-training passes: the reference runs four to five separate BMU
+ * passes with Python loops over the samples after the epoch loop (dbgsom/BaseSom.py:116-127); here
+ * the winners / distances of two device BMU searches stay in HBM and are reduced by these calls.
+ *
+ * dbgsom_node_stats  replaces  _calculate_topographic_error  dbgsom/BaseSom.py:924-953
+ *                              calculate_quantization_error  dbgsom/BaseSom.py:904-922
+ *                              _calculate_node_statistics    dbgsom/BaseSom.py:181-211
+ *   d_idx [N, idx_stride] winners (column 0 = BMU, column 1 = second BMU when idx_stride >= 2),
+ *   d_dist [N, dist_stride] distances (column 0), d_pos [M, 2] grid coordinates of the neurons.
+ *   d_out float64 [2 + 2M] = [#samples whose two BMUs are more than 1.5 apart on the grid,
+ *   sum of BMU distances, hit count per neuron, sum of exp(-d^2 / (2 bw^2)) / (bw sqrt(2 pi)) per neuron];
+ *   zeroed by the call.
+ */
+int dbgsom_node_stats(const int32_t* d_idx, int32_t idx_stride, const double* d_dist, int32_t dist_stride,
+                      int64_t N, const int32_t* d_pos, int32_t M, double bandwidth, double* d_out, void* stream);
+
+/* replaces  BaseSom._get_u_matrix  dbgsom/BaseSom.py:320-337:
+ * d_out[i] = sum_j d_colw[j] * ||W[i,:] - W[j,:]||_2  (float64, direct differences like scipy cdist);
+ * the caller passes d_colw[j] = degree(j) / sum of degrees (quirk Q12).  d_out is zeroed by the call. */
+int dbgsom_umatrix(const double* d_W, int32_t M, int32_t D, int64_t ldw, const double* d_colw, double* d_out,
+                   void* stream);
+
+/* replaces  SomClassifier._label_prototypes  dbgsom/SomClassifier.py:130-152 (the per-neuron class
+ * statistics it loops over the samples for): d_counts int32 [M, n_classes] class histogram per winner,
+ * d_first int64 [M, n_classes] smallest global sample index (sample_offset + row) per cell, INT64_MAX if
+ * empty -- statistics.mode returns the most frequent class met first.  Both are initialised by the call. */
+int dbgsom_label_hist(const int32_t* d_idx, int32_t idx_stride, const int32_t* d_labels, int64_t N,
+                      int64_t sample_offset, int32_t M, int32_t n_classes, int32_t* d_counts, int64_t* d_first,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * hop matrix on the device
+ * replaces  nx.floyd_warshall_numpy(self.som_)  dbgsom/BaseSom.py:401 (also :367, :235)
+ * d_adj int32 [M, 4]: neighbour indices of every neuron on the 4-connected grid graph, -1 = none.
+ * d_hop uint16 [M, ldh]: shortest-path hop counts, 0xFFFF = unreachable.  One BFS per source
+ * (unit edges), M <= DBGSOM_HOPS_MAX_M, else DBGSOM_E_UNSUPPORTED (the caller then uses its host BFS).
+ */
+#define DBGSOM_HOPS_MAX_M 28000
+int dbgsom_hops(const int32_t* d_adj, int32_t M, uint16_t* d_hop, int64_t ldh, void* stream);
 
 #ifdef __cplusplus
 }

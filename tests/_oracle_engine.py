@@ -70,6 +70,48 @@ class OracleEngine:
     def keep_rows(self, alive):
         self.W = self.W[alive]
 
+    def set_hops_from_topology(self, topo):
+        self.set_hops(topo.hop_matrix_u16())
+
+    def final_statistics(self, positions, degrees):
+        """numpy restatement of dbgsom/BaseSom.py:116-119 (TE :924-953, QE :904-922, node statistics
+        :181-211, u-matrix :320-337) on the oracle's BMU search."""
+        from scipy.spatial.distance import cdist
+
+        dist2, idx2 = self.bmu_train(2, previous=True)
+        m = self.W_prev.shape[0]
+        pos = np.asarray(positions, dtype=np.float64)
+        sep = pos[idx2[:, 0]] - pos[idx2[:, 1]]
+        te = float(np.count_nonzero(np.sqrt((sep * sep).sum(axis=1)) > 1.5))
+        winners, dist = idx2[:, 0], dist2[:, 0]
+        W = self.weights()
+        total = degrees.sum()
+        avg = (cdist(W, W) * degrees[None, :]).sum(axis=1) / total if total > 0 else np.full(len(W), np.nan)
+        bw = avg.mean()
+        hits = np.bincount(winners, minlength=m).astype(np.float64)
+        kern = np.exp(-(dist**2) / (2 * bw**2)) / (bw * np.sqrt(2 * np.pi))
+        dens = np.bincount(winners, weights=kern, minlength=m)
+        te, qe = self.allreduce_scalars([te, float(dist.sum())])
+        hits, dens = self.allreduce_arrays([hits, dens])
+        return {"te_count": te, "qe_sum": qe, "hits": hits, "dens_sum": dens, "avg_dist": avg, "weights": W, "n_rows": m}
+
+    def final_winners(self):
+        _, idx = self.bmu_train(1)
+        self._final = idx[:, 0].astype(np.int64)
+
+    def winners_host(self):
+        return self._final
+
+    def label_histogram(self, n_classes):
+        m = self.W.shape[0]
+        flat = self._final * n_classes + self.y.astype(np.int64)
+        counts = np.bincount(flat, minlength=m * n_classes).astype(np.float64)
+        first = np.full(m * n_classes, np.iinfo(np.int64).max, dtype=np.int64)
+        np.minimum.at(first, flat, np.arange(flat.size, dtype=np.int64) + self.sample_offset)
+        (counts,) = self.allreduce_arrays([counts])
+        (first,) = self.allreduce_arrays([first], op="min")
+        return counts.reshape(m, n_classes), first.reshape(m, n_classes)
+
     def bmu_train(self, n_bmu, previous=False):
         return self.bmu(self.X, self.W_prev if previous else self.W, n_bmu)
 

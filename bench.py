@@ -221,7 +221,10 @@ def run_ours(args, wl):
     n_global = eng.n_samples_global
     rows = np.random.default_rng(0).choice(n_global, m, replace=False)
     eng.init_map_from_rows(rows, capacity=m)
-    eng.set_hops(grid_hops(side))
+    # all-pairs hop counts of the side x side grid: BFS on the device from the adjacency table (dbgsom_hops)
+    from dbgsom_b200.topology import MapTopology
+
+    eng.set_hops_from_topology(MapTopology.full_grid(side, side))
 
     def barrier():
         if world > 1:

@@ -97,6 +97,24 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
       : "memory");
 }
+// same, delivered to the same shared-memory offset (and signalled on the same barrier offset) in every CTA of
+// the cluster named in cta_mask: one L2 read feeds all of them
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int x, int y,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, "
+      "{%3, %4}], [%2], %5;" ::"r"(smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -105,6 +123,14 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+// arrive on the barrier at this offset in every CTA of cta_mask once the MMAs issued so far have completed
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
 }
 // D[tmem] (+)= A[smem] . B[smem]^T, fp16 inputs, fp32 accumulate
 __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
@@ -236,7 +262,13 @@ struct Barriers {
   uint32_t tmem_base;
 };
 
-template <int NPASS, int NB, int BN, int RES_KB, int AKB>
+// CL: thread-block cluster size (1, 2 or 4).  The CTAs of a cluster work on different row tiles in lock
+// step and share every prototype tile: CTA r fetches rows [r * BN / CL, (r + 1) * BN / CL) of it and TMA
+// multicasts them into all CL shared memories, so the L2 -> SM traffic of the prototype stream (the whole
+// shadow matrix per 128 sample rows: 7 TB/s at config 3, which is what kept the tensor pipe at 78 %)
+// drops by CL.  A ring stage is free again when the MMA warps of ALL CL CTAs have consumed it (their
+// commits arrive on every CTA's `empty` barrier).
+template <int NPASS, int NB, int BN, int RES_KB, int AKB, int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     bmu_cand_tensor_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                            const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
@@ -265,6 +297,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int64_t n_row_tiles = ceil_div<int64_t>(N, BM);
+  // row tile of iteration `it`: clusters stride over groups of CL consecutive tiles; every CTA of a cluster runs
+  // the same number of iterations (tiles past the end are dummies: zero-filled loads, no output)
+  const uint32_t cl_rank = CL > 1 ? cluster_ctarank() : 0u;
+  const int64_t n_clusters = gridDim.x / CL;
+  const int64_t cluster_id = blockIdx.x / CL;
+  const int64_t n_iters = ceil_div<int64_t>(n_row_tiles, n_clusters * CL);
+  constexpr uint16_t cl_mask = (uint16_t)((1u << CL) - 1u);
+  auto tile_of = [&](int64_t it) { return (it * n_clusters + cluster_id) * CL + cl_rank; };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_xh);
@@ -277,7 +317,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&bars->full[s], 1);
-      mbar_init(&bars->empty[s], 1);
+      mbar_init(&bars->empty[s], CL);
     }
     mbar_init(&bars->a_full, 1);
     mbar_init(&bars->a_empty, 1);
@@ -295,6 +335,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // every CTA's barriers exist before a peer signals them
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
@@ -303,8 +344,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0, a_phase = 0;
-      for (int64_t rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x) {
-        const int row0 = (int)(rt * BM);
+      for (int64_t it = 0; it < n_iters; ++it) {
+        const int row0 = (int)(tile_of(it) * BM);
         if (XRES) {
           mbar_wait(&bars->a_empty, a_phase ^ 1);
           mbar_expect_tx(&bars->a_full, (uint32_t)(KB * C::NA * A_TILE_BYTES));
@@ -332,8 +373,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             mbar_wait(&bars->empty[stage], phase ^ 1);
             uint8_t* st = stages + stage * C::STAGE_BYTES;
             mbar_expect_tx(&bars->full[stage], (uint32_t)C::STAGE_BYTES);
-            tma_load_2d(st, &map_wh, &bars->full[stage], kb * BK, nt * BN);
-            if (NPASS == 3) tma_load_2d(st + C::B_TILE_BYTES, &map_wl, &bars->full[stage], kb * BK, nt * BN);
+            if (CL == 1) {
+              tma_load_2d(st, &map_wh, &bars->full[stage], kb * BK, nt * BN);
+              if (NPASS == 3) tma_load_2d(st + C::B_TILE_BYTES, &map_wl, &bars->full[stage], kb * BK, nt * BN);
+            } else {  // my 1/CL of the prototype tile, to everybody
+              const int part = C::B_TILE_BYTES / CL, prow = nt * BN + (int)cl_rank * (BN / CL);
+              tma_load_2d_mc(st + cl_rank * part, &map_wh, &bars->full[stage], kb * BK, prow, cl_mask);
+              if (NPASS == 3)
+                tma_load_2d_mc(st + C::B_TILE_BYTES + cl_rank * part, &map_wl, &bars->full[stage], kb * BK, prow, cl_mask);
+            }
             if (ASTREAM) {
               uint8_t* sa = st + C::NA * C::B_TILE_BYTES;
               tma_load_2d(sa, &map_xh, &bars->full[stage], kb * BK, row0);
@@ -353,7 +401,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       constexpr uint32_t idesc = instr_desc_f16(BM, BN);
       int stage = 0;
       uint32_t phase = 0, a_phase = 0, acc = 0, acc_phase = 0;
-      for (int64_t rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x) {
+      for (int64_t it = 0; it < n_iters; ++it) {
         if (XRES) {
           mbar_wait(&bars->a_full, a_phase);
           a_phase ^= 1;
@@ -373,7 +421,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 tc_cp_128x256b(tmem_a + AKB * (BK / 2) + kb * (BK / 2) + k * 8,
                                smem_desc_sw128(sa + A_TILE_BYTES + k * UMMA_K * 2));
             }
-            tc_commit(&bars->empty[stage]);
+            if (CL == 1) tc_commit(&bars->empty[stage]); else tc_commit_mc(&bars->empty[stage], cl_mask);
             if (++stage == C::STAGES) {
               stage = 0;
               phase ^= 1;
@@ -412,7 +460,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 }
               }
             }
-            tc_commit(&bars->empty[stage]);  // frees the smem stage once these MMAs have read it
+            // frees the smem stage (in every CTA of the cluster) once these MMAs have read it
+            if (CL == 1) tc_commit(&bars->empty[stage]); else tc_commit_mc(&bars->empty[stage], cl_mask);
             if (++stage == C::STAGES) {
               stage = 0;
               phase ^= 1;
@@ -447,8 +496,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const float* wn_src = wn_in_smem ? wn_smem : wnorm;
     asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
     uint32_t acc = 0, acc_phase = 0;
-    for (int64_t rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x) {
-      const int64_t row = rt * BM + t;
+    for (int64_t it = 0; it < n_iters; ++it) {
+      const int64_t row = tile_of(it) * BM + t;
       const float tau = row < N ? 2.f * tensor_score_bound(xnorm16[row], wmax, bound_coef) : 0.f;
       float m1 = kInf, m2 = kInf, thr = kInf, evicted = __int_as_float(0x7f800000);
       int n_app = 0;
@@ -571,6 +620,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // no CTA leaves while a peer may still write its shared memory or barriers
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
@@ -622,35 +672,79 @@ int sm_count() {
   return n;
 }
 
-template <int NPASS, int NB, int BN, int RES_KB, int AKB = 0>
-int launch_cfg(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t s) {
+template <int NPASS, int NB, int BN, int RES_KB, int AKB, int CL>
+int launch_cfg_cl(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t s) {
   using C = Cfg<NPASS, BN, RES_KB, AKB>;
   CUtensorMap mxh, mxl, mwh, mwl;
   int rc = make_map(&mxh, a.d_X16_hi, a.N, a.ld16, BM);
   if (rc) return rc;
-  rc = make_map(&mwh, a.d_W16_hi, a.Mpad, a.ld16, BN);
+  rc = make_map(&mwh, a.d_W16_hi, a.Mpad, a.ld16, BN / CL);
   if (rc) return rc;
   if (NPASS == 3) {
     rc = make_map(&mxl, a.d_X16_lo, a.N, a.ld16, BM);
     if (rc) return rc;
-    rc = make_map(&mwl, a.d_W16_lo, a.Mpad, a.ld16, BN);
+    rc = make_map(&mwl, a.d_W16_lo, a.Mpad, a.ld16, BN / CL);
     if (rc) return rc;
   } else {
     mxl = mxh;
     mwl = mwh;
   }
-  auto kern = bmu_cand_tensor_kernel<NPASS, NB, BN, RES_KB, AKB>;
+  auto kern = bmu_cand_tensor_kernel<NPASS, NB, BN, RES_KB, AKB, CL>;
   DBGSOM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   const int KB = (int)(a.ld16 / BK);
   const int NT = a.Mpad / BN;  // prototypes are permuted over all Mpad shadow rows
-  int64_t grid = ceil_div<int64_t>(a.N, BM);
-  if (grid > sm_count()) grid = sm_count();
-  kern<<<(unsigned)grid, TC_THREADS, C::SMEM_BYTES, s>>>(mxh, mxl, mwh, mwl, a.N, KB, NT, a.d_wnorm,
-                                                        a.d_proto_of_col, a.d_xnorm16, a.d_wmax,
-                                                        tensor_bound_coef(NPASS, a.bound_scale), a.d_idx, ws.cand_idx,
-                                                        ws.cand_count);
+  int64_t grid = round_up<int64_t>(ceil_div<int64_t>(a.N, BM), CL);
+  int64_t max_grid = sm_count() / CL * CL;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)max_grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CL > 1 ? 1 : 0;
+  if (CL > 1) {  // persistent kernel: no more clusters than can be resident at once (GPC boundaries)
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+      DBGSOM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 0));
+      if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) != cudaSuccess || max_clusters <= 0) {
+        (void)cudaGetLastError();
+        max_clusters = sm_count() / CL;
+      }
+    }
+    if (max_grid > (int64_t)max_clusters * CL) max_grid = (int64_t)max_clusters * CL;
+  }
+  if (grid > max_grid) grid = max_grid;
+  cfg.gridDim = dim3((unsigned)grid);
+  const float coef = tensor_bound_coef(NPASS, a.bound_scale);
+  DBGSOM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, mxh, mxl, mwh, mwl, a.N, KB, NT, a.d_wnorm, a.d_proto_of_col,
+                                     a.d_xnorm16, a.d_wmax, coef, a.d_idx, ws.cand_idx, ws.cand_count));
   DBGSOM_LAUNCH_CHECK();
   return DBGSOM_OK;
+}
+
+// cluster size: 2 by default (prototype tiles multicast to a CTA pair); DBGSOM_TC_CLUSTER = 1 | 2 | 4 overrides
+int cluster_size() {
+  static int cl = 0;
+  if (cl == 0) {
+    const char* e = getenv("DBGSOM_TC_CLUSTER");
+    cl = e ? atoi(e) : 2;
+    if (cl != 1 && cl != 2 && cl != 4) cl = 2;
+  }
+  return cl;
+}
+
+template <int NPASS, int NB, int BN, int RES_KB, int AKB = 0>
+int launch_cfg(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t s) {
+  // small problems (fewer row tiles than SMs) gain nothing from sharing
+  const int cl = ceil_div<int64_t>(a.N, BM) < sm_count() ? 1 : cluster_size();
+  if (cl == 4) return launch_cfg_cl<NPASS, NB, BN, RES_KB, AKB, 4>(a, ws, s);
+  if (cl == 2) return launch_cfg_cl<NPASS, NB, BN, RES_KB, AKB, 2>(a, ws, s);
+  return launch_cfg_cl<NPASS, NB, BN, RES_KB, AKB, 1>(a, ws, s);
 }
 
 template <int NPASS, int NB>

@@ -13,7 +13,7 @@ _LIB = None
 LIB_NAME = "libdbgsom_b200.so"
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_CAND = 8
 BMU_SIMT = 0
 BMU_TENSOR = 1
@@ -93,6 +93,8 @@ class SmoothArgs(C.Structure):
         ("d_change", c_void_p),
         ("d_workspace", c_void_p),
         ("workspace_bytes", c_size_t),
+        ("row_begin", c_int32),
+        ("row_end", c_int32),
     ]
 
 

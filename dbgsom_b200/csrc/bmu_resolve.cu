@@ -80,13 +80,17 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) bmu_resolve_kernel(
       ++n_ovf;
       bool full = true;
       if (NB == 1 && xnorm16 != nullptr) {
-        // More than kMaxCand prototypes lie within 2 * bound of the best approximate score, hence
-        // within 4 * bound of the true minimum: the best/second-best gap is below that.  If this is
-        // under the tie tolerance the approximate winner is as good as any (see dbgsom_b200.h).
+        // More than kMaxCand prototypes lie within 2 * bound of the best approximate score s1.  With s2 the
+        // second smallest approximate score and B the bound: every exact squared distance is >= s1 - B and
+        // the two prototypes behind s1, s2 are exactly <= s2 + B, so the exact best / second-best gap is at
+        // most (s2 - s1) + 2B and the exact minimum is at least db - 2B (db = exact distance of the approximate
+        // winner).  If that gap is under the tie tolerance the approximate winner is as good as any (see
+        // dbgsom_b200.h); the candidate search leaves s2 - s1 in the row's first candidate slot.
         const int jb = idx_out[row];
         const double db = sqdist_f64(x, W + (int64_t)jb * D, D, lane);
-        const float bound = tensor_score_bound(xnorm16[row], wmax, bound_coef) * inv_scale2;
-        if (4.0 * (double)bound <= (double)tie_rel * db) {
+        const double bound = (double)(tensor_score_bound(xnorm16[row], wmax, bound_coef) * inv_scale2);
+        const double gap = (double)(__int_as_float(cand_idx[row * kMaxCand]) * inv_scale2) + 2.0 * bound;
+        if (jb >= 0 && gap <= (double)tie_rel * (db - 2.0 * bound)) {
           top.offer(db, jb);
           full = false;
         }
@@ -121,71 +125,83 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) bmu_resolve_kernel(
   }
 }
 
-// Full re-score of queued samples: one CTA takes eight samples (in shared memory) and streams all
-// M float64 prototype rows once for the eight of them; warps stripe the prototypes, lanes the features.
-constexpr int RS_ROWS = 8;
-template <int NB>
+// Full re-score of queued samples: one CTA takes R samples, converts them to float64 in shared memory
+// once, and streams all M float64 prototype rows once for the R of them.  A warp scores RS_P prototypes
+// per iteration against all R samples (R x RS_P accumulators in registers), so every shared-memory load
+// of a sample element feeds RS_P subtract/FMA pairs and every prototype element R of them: the float64
+// pipe is the limiter, not the load ports (the first version converted float -> double per use and was
+// bound by the conversion unit at ~20 % of the float64 rate).
+constexpr int RS_P = 4;
+template <int NB, int R>
 __global__ void __launch_bounds__(256) bmu_rescan_kernel(const float* __restrict__ X, int64_t ldx, int D,
                                                         const double* __restrict__ W, int M,
                                                         const int32_t* __restrict__ rescan_count,
                                                         const int32_t* __restrict__ rescan_rows, int want_dist,
                                                         int32_t* __restrict__ idx_out, double* __restrict__ dist_out) {
-  extern __shared__ __align__(16) float xs[];  // [RS_ROWS][D]
-  __shared__ double m_d[8][RS_ROWS][2];
-  __shared__ int m_i[8][RS_ROWS][2];
-  __shared__ int row_id[RS_ROWS];
+  extern __shared__ __align__(16) double xs[];  // [R][D]
+  __shared__ double m_d[8][R][2];
+  __shared__ int m_i[8][R][2];
+  __shared__ int row_id[R];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = *rescan_count;
-  const int groups = ceil_div(n, RS_ROWS);
+  const int groups = ceil_div(n, R);
   for (int g = blockIdx.x; g < groups; g += gridDim.x) {
     __syncthreads();
-    if (threadIdx.x < RS_ROWS) {
-      const int q = g * RS_ROWS + threadIdx.x;
+    if (threadIdx.x < R) {
+      const int q = g * R + threadIdx.x;
       row_id[threadIdx.x] = q < n ? rescan_rows[q] : -1;
     }
     __syncthreads();
-    for (int e = threadIdx.x * 4; e < RS_ROWS * D; e += 256 * 4) {
+    for (int e = threadIdx.x; e < R * D; e += 256) {
       const int r = e / D, d = e % D;
       const int rid = row_id[r];
-      const float4 v = rid >= 0 ? *reinterpret_cast<const float4*>(X + (int64_t)rid * ldx + d)
-                                : make_float4(0.f, 0.f, 0.f, 0.f);
-      *reinterpret_cast<float4*>(xs + e) = v;
+      xs[e] = rid >= 0 ? (double)X[(int64_t)rid * ldx + d] : 0.0;
     }
     __syncthreads();
-    Top2 top[RS_ROWS];
+    Top2 top[R];
 #pragma unroll
-    for (int r = 0; r < RS_ROWS; ++r) top[r].init();
-    for (int j = warp; j < M; j += 8) {
-      double acc[RS_ROWS];
+    for (int r = 0; r < R; ++r) top[r].init();
+    for (int j0 = warp * RS_P; j0 < M; j0 += 8 * RS_P) {
+      double acc[R][RS_P];
 #pragma unroll
-      for (int r = 0; r < RS_ROWS; ++r) acc[r] = 0.0;
-      const double* w = W + (int64_t)j * D;
-      for (int d = lane * 4; d < D; d += 128) {
-        const double2 w0 = *reinterpret_cast<const double2*>(w + d);
-        const double2 w1 = *reinterpret_cast<const double2*>(w + d + 2);
+      for (int r = 0; r < R; ++r)
 #pragma unroll
-        for (int r = 0; r < RS_ROWS; ++r) {
-          const float4 xv = *reinterpret_cast<const float4*>(xs + r * D + d);
-          const double a = (double)xv.x - w0.x, b = (double)xv.y - w0.y;
-          const double c = (double)xv.z - w1.x, e2 = (double)xv.w - w1.y;
-          acc[r] = fma(a, a, acc[r]);
-          acc[r] = fma(b, b, acc[r]);
-          acc[r] = fma(c, c, acc[r]);
-          acc[r] = fma(e2, e2, acc[r]);
+        for (int p = 0; p < RS_P; ++p) acc[r][p] = 0.0;
+      for (int d = lane * 2; d < D; d += 64) {  // D % 4 == 0: pairs never straddle the row end
+        double2 w[RS_P];
+#pragma unroll
+        for (int p = 0; p < RS_P; ++p) {
+          const int j = j0 + p < M ? j0 + p : M - 1;
+          w[p] = *reinterpret_cast<const double2*>(W + (int64_t)j * D + d);
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const double2 xv = *reinterpret_cast<const double2*>(xs + r * D + d);
+#pragma unroll
+          for (int p = 0; p < RS_P; ++p) {
+            const double a = xv.x - w[p].x, b = xv.y - w[p].y;
+            acc[r][p] = fma(a, a, acc[r][p]);
+            acc[r][p] = fma(b, b, acc[r][p]);
+          }
         }
       }
 #pragma unroll
-      for (int r = 0; r < RS_ROWS; ++r) top[r].offer(warp_sum(acc[r]), j);
+      for (int p = 0; p < RS_P; ++p) {
+        if (j0 + p < M) {  // warp-uniform
+#pragma unroll
+          for (int r = 0; r < R; ++r) top[r].offer(warp_sum(acc[r][p]), j0 + p);
+        }
+      }
     }
     if (lane == 0) {
 #pragma unroll
-      for (int r = 0; r < RS_ROWS; ++r) {
+      for (int r = 0; r < R; ++r) {
         m_d[warp][r][0] = top[r].d1; m_d[warp][r][1] = top[r].d2;
         m_i[warp][r][0] = top[r].i1; m_i[warp][r][1] = top[r].i2;
       }
     }
     __syncthreads();
-    if (threadIdx.x < RS_ROWS && row_id[threadIdx.x] >= 0) {
+    if (threadIdx.x < R && row_id[threadIdx.x] >= 0) {
       const int r = threadIdx.x;
       Top2 t;
       t.init();
@@ -204,6 +220,18 @@ __global__ void __launch_bounds__(256) bmu_rescan_kernel(const float* __restrict
   }
 }
 
+template <int NB, int R>
+int launch_rescan(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t s) {
+  const size_t smem = (size_t)R * a.D * sizeof(double);
+  auto kern = bmu_rescan_kernel<NB, R>;
+  DBGSOM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int per_sm = smem > 100 * 1024 ? 1 : 2;
+  kern<<<148 * per_sm, 256, smem, s>>>(a.d_X, a.ldx, a.D, a.d_W, a.M, ws.rescan_count, ws.rescan_rows, a.want_dist,
+                                       a.d_idx, a.d_dist);
+  DBGSOM_LAUNCH_CHECK();
+  return DBGSOM_OK;
+}
+
 }  // namespace
 
 int launch_bmu_resolve(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t s) {
@@ -216,27 +244,19 @@ int launch_bmu_resolve(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStr
   const float inv_s2 = a.scale > 0.f ? 1.f / (a.scale * a.scale) : 1.f;
   const float tie = a.tie_rel > 0.f ? a.tie_rel : 1e-6f;
   DBGSOM_CUDA_TRY(cudaMemsetAsync(ws.rescan_count, 0, sizeof(int32_t), s));
-  const size_t rs_smem = (size_t)RS_ROWS * a.D * sizeof(float);
-  const int rs_grid = 148 * 2;
+  const bool wide = (size_t)8 * a.D * sizeof(double) > 200 * 1024;  // D > 3200: four samples per CTA
   if (a.n_bmu == 1) {
     bmu_resolve_kernel<1><<<(unsigned)blocks, WARPS_PER_BLOCK * 32, 0, s>>>(
         a.d_X, a.N, a.D, a.ldx, a.d_W, a.M, ws.cand_idx, ws.cand_count, a.want_dist, a.d_idx, a.d_dist, stats, xn,
         a.d_wmax, coef, inv_s2, tie, ws.rescan_count, ws.rescan_rows);
     DBGSOM_LAUNCH_CHECK();
-    DBGSOM_CUDA_TRY(cudaFuncSetAttribute(bmu_rescan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
-    bmu_rescan_kernel<1><<<rs_grid, 256, rs_smem, s>>>(a.d_X, a.ldx, a.D, a.d_W, a.M, ws.rescan_count, ws.rescan_rows,
-                                                      a.want_dist, a.d_idx, a.d_dist);
-  } else {
-    bmu_resolve_kernel<2><<<(unsigned)blocks, WARPS_PER_BLOCK * 32, 0, s>>>(
-        a.d_X, a.N, a.D, a.ldx, a.d_W, a.M, ws.cand_idx, ws.cand_count, a.want_dist, a.d_idx, a.d_dist, stats, xn,
-        a.d_wmax, coef, inv_s2, tie, ws.rescan_count, ws.rescan_rows);
-    DBGSOM_LAUNCH_CHECK();
-    DBGSOM_CUDA_TRY(cudaFuncSetAttribute(bmu_rescan_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
-    bmu_rescan_kernel<2><<<rs_grid, 256, rs_smem, s>>>(a.d_X, a.ldx, a.D, a.d_W, a.M, ws.rescan_count, ws.rescan_rows,
-                                                      a.want_dist, a.d_idx, a.d_dist);
+    return wide ? launch_rescan<1, 4>(a, ws, s) : launch_rescan<1, 8>(a, ws, s);
   }
+  bmu_resolve_kernel<2><<<(unsigned)blocks, WARPS_PER_BLOCK * 32, 0, s>>>(
+      a.d_X, a.N, a.D, a.ldx, a.d_W, a.M, ws.cand_idx, ws.cand_count, a.want_dist, a.d_idx, a.d_dist, stats, xn,
+      a.d_wmax, coef, inv_s2, tie, ws.rescan_count, ws.rescan_rows);
   DBGSOM_LAUNCH_CHECK();
-  return DBGSOM_OK;
+  return wide ? launch_rescan<2, 4>(a, ws, s) : launch_rescan<2, 8>(a, ws, s);
 }
 
 }  // namespace dbgsom

@@ -586,7 +586,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         const float gthr = gm < 1.0e38f ? gm + tau : kInf;
         int out[kMaxCand];
         int cnt = 0, best = -1;
-        float bv = __int_as_float(0x7f800000);
+        float bv = __int_as_float(0x7f800000), sv = __int_as_float(0x7f800000);  // two smallest scores kept
         bool overflow = ev <= gthr;
 #pragma unroll 1
         for (int q = 0; q < EPI_SUBS; ++q) {
@@ -598,8 +598,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
               if (cnt < kMaxCand) out[cnt] = jj;
               ++cnt;
               if (v < bv || (v == bv && jj < best)) {
+                sv = bv;
                 bv = v;
                 best = jj;
+              } else if (v < sv) {
+                sv = v;
               }
             }
           }
@@ -609,6 +612,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           const int valid = overflow ? 0 : cnt;
 #pragma unroll
           for (int q = 0; q < kMaxCand; ++q) cand_idx[row * kMaxCand + q] = q < valid ? out[q] : -1;
+          // a flagged row has no candidate list; its first slot carries the gap between the two smallest
+          // approximate scores instead (>= 0, float bits), which tightens the near-tie test of the re-score
+          if (overflow) cand_idx[row * kMaxCand] = __float_as_int(fmaxf(sv - bv, 0.f));
           cand_count[row] = (uint8_t)(overflow ? DBGSOM_CAND_OVERFLOW : cnt);
           idx_out[row * NB] = best;
         }

@@ -131,6 +131,7 @@ int dbgsom_smooth(const dbgsom_smooth_args* a, void* stream) {
   if (!a || !a->d_part || !a->d_hop || !a->d_kernel_lut || !a->d_W_in || !a->d_W_out || !a->d_change || !a->d_workspace)
     return DBGSOM_E_BADARG;
   if (a->M <= 0 || a->D <= 0 || a->ldh < a->M || a->lut_len <= 0 || a->d_W_in == a->d_W_out) return DBGSOM_E_BADARG;
+  if (a->row_end > a->row_begin && (a->row_begin < 0 || a->row_end > a->M)) return DBGSOM_E_BADARG;
   if (a->workspace_bytes < smooth_workspace_bytes(a->M, a->D)) return DBGSOM_E_WORKSPACE;
   return run_smooth(*a, as_stream(stream));
 }

@@ -15,7 +15,9 @@ namespace {
 // single CTA: rank live neurons (n > 0), src[r] = index of the r-th live neuron (or -1)
 constexpr int RANK_THREADS = 1024;
 __global__ void __launch_bounds__(RANK_THREADS) live_rank_kernel(const double* __restrict__ n, int M, int pack,
-                                                                int32_t* __restrict__ src) {
+                                                                int32_t* __restrict__ src, int32_t* __restrict__ live_list,
+                                                                double* __restrict__ n_live_vals,
+                                                                int32_t* __restrict__ n_live) {
   __shared__ int32_t warp_tot[32];
   __shared__ int32_t carry_sh;
   if (threadIdx.x == 0) carry_sh = 0;
@@ -47,60 +49,78 @@ __global__ void __launch_bounds__(RANK_THREADS) live_rank_kernel(const double* _
     const int carry = carry_sh;
     const int rank = carry + (warp ? warp_tot[warp - 1] : 0) + v - live;
     if (pack && live) src[rank] = j;  // rank <= j: never clobbers a default written by a later pass
+    if (live) {  // compact list of the neurons that won samples: the only columns of H that matter
+      live_list[rank] = j;
+      n_live_vals[rank] = n[j];
+    }
     __syncthreads();
     if (threadIdx.x == RANK_THREADS - 1) carry_sh = carry + warp_tot[31];
     __syncthreads();
   }
+  if (threadIdx.x == 0) *n_live = carry_sh;
 }
 
-// B[j, :] = n_j * Sk[src_j, :] / sk[src_j]   (0 when src_j < 0);  den[i] = sum_j H_ij n_j
+// Only neurons with samples (n_j > 0) contribute to either sum of the update, so both run over the compact
+// list live[0..L):  Bc[r, :] = n_j * C'[j, :],  j = live[r],  C'[j] = Sk[src_j] / sk[src_j]  (0 when src_j < 0:
+// with packed rows a live neuron beyond the first L rows has an all-zero centre, quirk Q1).
 __global__ void __launch_bounds__(256) weighted_centres_kernel(const double* __restrict__ part, int M, int D,
                                                               const int32_t* __restrict__ src,
-                                                              double* __restrict__ B) {
+                                                              const int32_t* __restrict__ live,
+                                                              const int32_t* __restrict__ n_live,
+                                                              double* __restrict__ Bc) {
   const double* Sk = part;
   const double* sk = part + (int64_t)M * D;
   const double* n = sk + M;
-  const int64_t total = (int64_t)M * D;
+  const int64_t total = (int64_t)(*n_live) * D;
   for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (int64_t)gridDim.x * 256) {
-    const int j = (int)(e / D), d = (int)(e % D);
+    const int r = (int)(e / D), d = (int)(e % D);
+    const int j = live[r];
     const int sj = src[j];
-    B[e] = sj >= 0 ? n[j] * (Sk[(int64_t)sj * D + d] / sk[sj]) : 0.0;
+    Bc[e] = sj >= 0 ? n[j] * (Sk[(int64_t)sj * D + d] / sk[sj]) : 0.0;
   }
 }
 
+// den[i] = sum_r H[i, live[r]] n[live[r]]  for the rows [row_begin, row_end)
 __global__ void __launch_bounds__(256) denominator_kernel(const uint16_t* __restrict__ hop, int64_t ldh,
                                                          const double* __restrict__ lut, int lut_len,
-                                                         const double* __restrict__ n, int M,
-                                                         double* __restrict__ den) {
+                                                         const int32_t* __restrict__ live,
+                                                         const double* __restrict__ n_live_vals,
+                                                         const int32_t* __restrict__ n_live, int row_begin,
+                                                         int row_end, double* __restrict__ den) {
   const int lane = threadIdx.x & 31;
-  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (i >= M) return;
+  const int i = row_begin + blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= row_end) return;
+  const int L = *n_live;
   double acc = 0.0;
-  for (int j = lane; j < M; j += 32) {
-    const unsigned h = hop[(int64_t)i * ldh + j];
-    if (h < (unsigned)lut_len) acc = fma(lut[h], n[j], acc);
+  for (int r = lane; r < L; r += 32) {
+    const unsigned h = hop[(int64_t)i * ldh + live[r]];
+    if (h < (unsigned)lut_len) acc = fma(lut[h], n_live_vals[r], acc);
   }
   acc = warp_sum(acc);
   if (lane == 0) den[i] = acc;
 }
 
 // ------------------------------------------------------------------------------------------ GEMM
-// W_out[i, d] = (sum_j H_ij B[j, d]) / den[i];   tile 128 (i) x 64 (d), 16-wide j steps, 8 x 4 outputs per
-// thread (6 shared-memory vector loads per 32 DFMA keeps the float64 pipe, not the LDS port, the limiter).
+// W_out[i, d] = (sum_r H[i, live[r]] Bc[r, d]) / den[i] for rows [row_begin, row_end);   tile 128 (i) x 64 (d),
+// 16-wide steps over the live list, 8 x 4 outputs per thread (6 shared-memory vector loads per 32 DFMA keeps
+// the float64 pipe, not the LDS port, the limiter).
 constexpr int TI = 128, TD = 64, TJ = 16;
 __global__ void __launch_bounds__(256) smooth_gemm_kernel(const uint16_t* __restrict__ hop, int64_t ldh,
                                                          const double* __restrict__ lut, int lut_len,
                                                          const double* __restrict__ B, const double* __restrict__ den,
-                                                         int M, int D, double* __restrict__ W_out) {
+                                                         const int32_t* __restrict__ live,
+                                                         const int32_t* __restrict__ n_live, int row_begin,
+                                                         int row_end, int D, double* __restrict__ W_out) {
   __shared__ __align__(16) double Hs[TJ][TI];
   __shared__ __align__(16) double Bs[TJ][TD];
   const int tid = threadIdx.x;
   const int tx = tid % 16;  // 4 columns
   const int ty = tid / 16;  // 8 rows
-  const int i0 = blockIdx.y * TI, d0 = blockIdx.x * TD;
+  const int i0 = row_begin + blockIdx.y * TI, d0 = blockIdx.x * TD;
+  const int L = *n_live;
   double acc[8][4] = {};
 
-  for (int j0 = 0; j0 < M; j0 += TJ) {
+  for (int j0 = 0; j0 < L; j0 += TJ) {
     // H tile: 128 x 16 entries, 8 per thread: thread -> (i = tid / 2, 8 consecutive j)
     {
       const int ii = tid >> 1, jj = (tid & 1) * 8;
@@ -109,8 +129,8 @@ __global__ void __launch_bounds__(256) smooth_gemm_kernel(const uint16_t* __rest
       for (int q = 0; q < 8; ++q) {
         const int j = j0 + jj + q;
         double h = 0.0;
-        if (i < M && j < M) {
-          const unsigned hp = hop[(int64_t)i * ldh + j];
+        if (i < row_end && j < L) {
+          const unsigned hp = hop[(int64_t)i * ldh + live[j]];
           if (hp < (unsigned)lut_len) h = lut[hp];
         }
         Hs[jj + q][ii] = h;
@@ -122,7 +142,7 @@ __global__ void __launch_bounds__(256) smooth_gemm_kernel(const uint16_t* __rest
       const int e = tid + q * 256;
       const int jj = e / TD, dd = e % TD;
       const int j = j0 + jj, d = d0 + dd;
-      Bs[jj][dd] = (j < M && d < D) ? B[(int64_t)j * D + d] : 0.0;
+      Bs[jj][dd] = (j < L && d < D) ? B[(int64_t)j * D + d] : 0.0;
     }
     __syncthreads();
 #pragma unroll
@@ -149,7 +169,7 @@ __global__ void __launch_bounds__(256) smooth_gemm_kernel(const uint16_t* __rest
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
     const int i = i0 + ty * 8 + r;
-    if (i >= M) continue;
+    if (i >= row_end) continue;
     const double dn = den[i];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -161,10 +181,10 @@ __global__ void __launch_bounds__(256) smooth_gemm_kernel(const uint16_t* __rest
 
 // change += ||W_in[i] - W_out[i]||_2, one warp per row
 __global__ void __launch_bounds__(256) change_kernel(const double* __restrict__ W_in, const double* __restrict__ W_out,
-                                                    int M, int D, double* __restrict__ change) {
+                                                    int row_begin, int row_end, int D, double* __restrict__ change) {
   const int lane = threadIdx.x & 31;
-  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (i >= M) return;
+  const int i = row_begin + blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= row_end) return;
   double acc = 0.0;
   for (int d = lane; d < D; d += 32) {
     const double t = W_in[(int64_t)i * D + d] - W_out[(int64_t)i * D + d];
@@ -177,18 +197,23 @@ __global__ void __launch_bounds__(256) change_kernel(const double* __restrict__ 
 }  // namespace
 
 struct SmoothWorkspace {
-  int32_t* src;
-  double* den;
-  double* B;
+  int32_t *src, *live, *n_live;
+  double *den, *n_live_vals, *B;
   static size_t bytes(int M, int D) {
-    return round_up<size_t>((size_t)M * 4, 256) + round_up<size_t>((size_t)M * 8, 256) + (size_t)M * D * 8;
+    return 2 * round_up<size_t>((size_t)M * 4, 256) + 256 + 2 * round_up<size_t>((size_t)M * 8, 256) + (size_t)M * D * 8;
   }
   static SmoothWorkspace carve(void* base, int M, int D) {
     SmoothWorkspace w;
     uint8_t* p = reinterpret_cast<uint8_t*>(base);
     w.src = reinterpret_cast<int32_t*>(p);
     p += round_up<size_t>((size_t)M * 4, 256);
+    w.live = reinterpret_cast<int32_t*>(p);
+    p += round_up<size_t>((size_t)M * 4, 256);
+    w.n_live = reinterpret_cast<int32_t*>(p);
+    p += 256;
     w.den = reinterpret_cast<double*>(p);
+    p += round_up<size_t>((size_t)M * 8, 256);
+    w.n_live_vals = reinterpret_cast<double*>(p);
     p += round_up<size_t>((size_t)M * 8, 256);
     w.B = reinterpret_cast<double*>(p);
     return w;
@@ -200,24 +225,29 @@ size_t smooth_workspace_bytes(int M, int D) { return SmoothWorkspace::bytes(M, D
 int run_smooth(const dbgsom_smooth_args& a, cudaStream_t s) {
   const SmoothWorkspace ws = SmoothWorkspace::carve(a.d_workspace, a.M, a.D);
   const int M = a.M, D = a.D;
+  const int r0 = a.row_end > a.row_begin ? a.row_begin : 0;
+  const int r1 = a.row_end > a.row_begin ? a.row_end : M;
+  const int rows = r1 - r0;
   const double* n = a.d_part + (int64_t)M * D + M;
   DBGSOM_CUDA_TRY(cudaMemsetAsync(a.d_change, 0, sizeof(double), s));
-  live_rank_kernel<<<1, RANK_THREADS, 0, s>>>(n, M, a.pack_rows, ws.src);
+  live_rank_kernel<<<1, RANK_THREADS, 0, s>>>(n, M, a.pack_rows, ws.src, ws.live, ws.n_live_vals, ws.n_live);
   DBGSOM_LAUNCH_CHECK();
   {
     int64_t blocks = ceil_div<int64_t>((int64_t)M * D, 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    weighted_centres_kernel<<<(unsigned)blocks, 256, 0, s>>>(a.d_part, M, D, ws.src, ws.B);
+    weighted_centres_kernel<<<(unsigned)blocks, 256, 0, s>>>(a.d_part, M, D, ws.src, ws.live, ws.n_live, ws.B);
     DBGSOM_LAUNCH_CHECK();
   }
-  denominator_kernel<<<ceil_div(M, 8), 256, 0, s>>>(a.d_hop, a.ldh, a.d_kernel_lut, a.lut_len, n, M, ws.den);
+  denominator_kernel<<<ceil_div(rows, 8), 256, 0, s>>>(a.d_hop, a.ldh, a.d_kernel_lut, a.lut_len, ws.live,
+                                                       ws.n_live_vals, ws.n_live, r0, r1, ws.den);
   DBGSOM_LAUNCH_CHECK();
   {
-    const dim3 grid(ceil_div(D, TD), ceil_div(M, TI));
-    smooth_gemm_kernel<<<grid, 256, 0, s>>>(a.d_hop, a.ldh, a.d_kernel_lut, a.lut_len, ws.B, ws.den, M, D, a.d_W_out);
+    const dim3 grid(ceil_div(D, TD), ceil_div(rows, TI));
+    smooth_gemm_kernel<<<grid, 256, 0, s>>>(a.d_hop, a.ldh, a.d_kernel_lut, a.lut_len, ws.B, ws.den, ws.live, ws.n_live,
+                                            r0, r1, D, a.d_W_out);
     DBGSOM_LAUNCH_CHECK();
   }
-  change_kernel<<<ceil_div(M, 8), 256, 0, s>>>(a.d_W_in, a.d_W_out, M, D, a.d_change);
+  change_kernel<<<ceil_div(rows, 8), 256, 0, s>>>(a.d_W_in, a.d_W_out, r0, r1, D, a.d_change);
   DBGSOM_LAUNCH_CHECK();
   return DBGSOM_OK;
 }

@@ -12,6 +12,7 @@ There is deliberately no CPU path here: constructing the engine without CUDA rai
 from __future__ import annotations
 
 import math
+import os
 from typing import Sequence
 
 import numpy as np
@@ -66,6 +67,9 @@ class Comm:
 
 class DeviceEngine:
     """One fit's worth of device state.  See module docstring."""
+
+    # M^2 D above which the smoothing rows are split over the ranks (DBGSOM_K3_SHARD_MIN_WORK overrides; tests)
+    K3_SHARD_MIN_WORK = int(os.environ.get("DBGSOM_K3_SHARD_MIN_WORK", 1 << 36))
 
     def __init__(
         self,
@@ -549,9 +553,26 @@ class DeviceEngine:
         sm.d_W_in, sm.d_W_out, sm.d_change = cur.data_ptr(), out.data_ptr(), self.change.data_ptr()
         ws2 = self._workspace("smooth", self.lib.dbgsom_smooth_workspace_bytes(m, self.ldx))
         sm.d_workspace, sm.workspace_bytes = ws2.data_ptr(), ws2.numel()
+        # Large maps on several GPUs: every rank smooths its own row range and the rows are all-gathered
+        # (M^2 D flops / world instead of redundantly; the gathered copies are bit-identical on all ranks).
+        world = self.comm.world if self.comm.enabled else 1
+        rows_per = -(-m // world)
+        shard_rows = world > 1 and m * m * self.ldx >= self.K3_SHARD_MIN_WORK and rows_per * world <= out.shape[0]
+        if shard_rows:
+            sm.row_begin = min(self.comm.rank * rows_per, m)
+            sm.row_end = min(sm.row_begin + rows_per, m)
         with self._Phase(self, "smooth"):
-            nat.check(self.lib.dbgsom_smooth(sm, self._stream()), "dbgsom_smooth")
+            if not shard_rows or sm.row_end > sm.row_begin:
+                nat.check(self.lib.dbgsom_smooth(sm, self._stream()), "dbgsom_smooth")
+            else:
+                self.change.zero_()
         self.launches += 6
+        if shard_rows:
+            with self._Phase(self, "allgather"):
+                flat = out[: rows_per * world]
+                mine = flat[self.comm.rank * rows_per : (self.comm.rank + 1) * rows_per]
+                self.comm.dist.all_gather_into_tensor(flat, mine)
+                self.comm.allreduce_(self.change)
         self.cur ^= 1
         self.n_previous_rows = m
 

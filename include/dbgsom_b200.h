@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define DBGSOM_ABI_VERSION 2
+#define DBGSOM_ABI_VERSION 3
 
 #define DBGSOM_OK 0
 #define DBGSOM_E_BADARG (-1)      /* null pointer, non-positive size, bad enum             */
@@ -216,6 +216,7 @@ int dbgsom_accumulate(const dbgsom_accumulate_args* args, void* stream);
  * d_change[0] = sum_i ||W_in[i,:] - W_out[i,:]||_2   (the call zeroes it first).
  * d_kernel_lut [lut_len] float64 holds exp(-h^2 / (2 sigma^2)) for h = 0..lut_len-1, computed by
  * the host with the same numpy expression as the reference; hop 0xFFFF or >= lut_len gives H = 0.
+ * Both sums run over the neurons with n_j > 0 only (the others contribute exact zeros).
  * All arithmetic is float64.
  */
 typedef struct dbgsom_smooth_args {
@@ -232,6 +233,9 @@ typedef struct dbgsom_smooth_args {
   double* d_change;          /* [1] */
   void* d_workspace;
   size_t workspace_bytes;
+  int32_t row_begin;         /* rows [row_begin, row_end) of W_out are written and summed into d_change; */
+  int32_t row_end;           /* row_end <= row_begin means all M rows.  Sharded maps: every rank takes a row range
+                                and all-gathers W_out (the sums over the neurons are not split). */
 } dbgsom_smooth_args;
 
 size_t dbgsom_smooth_workspace_bytes(int32_t M, int32_t D);

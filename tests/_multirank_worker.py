@@ -1,0 +1,70 @@
+"""Worker of tests/test_gpu_multirank.py: run under torchrun with one rank per GPU.
+
+Every rank trains on its contiguous shard through the distributed engine (NCCL all-reduce of the partial
+sums, optionally row-sharded smoothing + all-gather); rank 0 repeats the same epochs on the full data with
+a single-GPU engine and compares."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import _datasets  # noqa: E402
+from dbgsom_b200.engine import DeviceEngine  # noqa: E402
+from dbgsom_b200.topology import MapTopology  # noqa: E402
+
+
+def run(eng, X, y, c, rows, topo, sigmas):
+    eng.load_data(X, y, c)
+    eng.init_map_from_rows(rows, capacity=len(topo))
+    eng.set_hops_from_topology(topo)
+    outs = [eng.epoch(s, True, False) for s in sigmas]
+    st = eng.final_statistics(topo.positions(), topo.degrees())
+    eng.final_winners()
+    hist = eng.label_histogram(c)
+    return outs, eng.weights(), st, hist
+
+
+def main():
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    n, d, c = 60000, 96, 5
+    X, y = _datasets.gmm(n, d, c, 7, return_labels=True)
+    topo = MapTopology.full_grid(9, 11)
+    rows = np.random.default_rng(0).choice(n, len(topo), replace=False)
+    sigmas = [2.0, 1.6, 1.2]
+    per = -(-n // world)
+    sl = slice(rank * per, min(n, (rank + 1) * per))
+    eng = DeviceEngine(device=f"cuda:{local}", distributed=True, bmu_backend=os.environ.get("MR_BACKEND", "auto"))
+    outs, W, st, hist = run(eng, X[sl], y[sl], c, rows, topo, sigmas)
+    eng.close()
+    ok = True
+    if rank == 0:
+        ref = DeviceEngine(device="cuda:0", distributed=False, bmu_backend=os.environ.get("MR_BACKEND", "auto"))
+        r_outs, r_W, r_st, r_hist = run(ref, X, y, c, rows, topo, sigmas)
+        ref.close()
+        for a, b in zip(outs, r_outs):
+            np.testing.assert_array_equal(a["counts"], b["counts"])
+            np.testing.assert_allclose(a["error"], b["error"], rtol=1e-10)
+            assert abs(a["change"] - b["change"]) <= 1e-9 * abs(b["change"])
+        np.testing.assert_allclose(W, r_W, rtol=1e-10, atol=1e-12)
+        for k in ("te_count", "qe_sum"):
+            assert abs(st[k] - r_st[k]) <= 1e-10 * max(1.0, abs(r_st[k])), k
+        np.testing.assert_array_equal(st["hits"], r_st["hits"])
+        np.testing.assert_allclose(st["dens_sum"], r_st["dens_sum"], rtol=1e-9)
+        np.testing.assert_array_equal(hist[0], r_hist[0])
+        np.testing.assert_array_equal(hist[1], r_hist[1])
+        print("MULTIRANK_OK world=%d shard_min_work=%s" % (world, os.environ.get("DBGSOM_K3_SHARD_MIN_WORK")), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -59,7 +59,7 @@ def test_struct_sizes_match_the_c_layout():
     # 64-bit layout of the three argument structs (guards against field drift in the binding)
     assert ctypes.sizeof(nat.BmuArgs) == 200
     assert ctypes.sizeof(nat.AccumulateArgs) == 112
-    assert ctypes.sizeof(nat.SmoothArgs) == 88
+    assert ctypes.sizeof(nat.SmoothArgs) == 96
 
 
 def test_engine_refuses_to_run_without_cuda():

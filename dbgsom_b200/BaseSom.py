@@ -339,19 +339,16 @@ class BaseSom(BaseEstimator):
     def transform(self, X, y=None) -> np.ndarray:
         """Non-negative sparse code of each sample over the normalised prototypes.
 
-        Host path, identical to dbgsom/BaseSom.py:241-268 (scikit-learn `SparseCoder`,
-        LARS); not part of the training epoch.
+        Same result as dbgsom/BaseSom.py:241-268 (scikit-learn `SparseCoder`, `lasso_lars`, positive, alpha 0)
+        computed on the device: the LARS-lasso path of every sample runs in `dbgsom_sparse_code`
+        (csrc/lars_core.cuh restates scikit-learn's solver).
         """
-        from sklearn.decomposition import SparseCoder
         from sklearn.preprocessing import normalize
 
         check_is_fitted(self)
         X = check_array(X, dtype=[np.float64, np.float32])
-        coder = SparseCoder(
-            dictionary=normalize(self.weights_),
-            n_jobs=self.n_jobs,
-            positive_code=True,
-            transform_alpha=0,
-            transform_algorithm="lasso_lars",
-        )
-        return coder.transform(normalize(X))
+        engine = self._make_engine(distributed=False)
+        try:
+            return engine.sparse_code(normalize(X), normalize(self.weights_))
+        finally:
+            engine.close()

@@ -13,7 +13,7 @@ _LIB = None
 LIB_NAME = "libdbgsom_b200.so"
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_CAND = 8
 BMU_SIMT = 0
 BMU_TENSOR = 1
@@ -131,6 +131,12 @@ SIGNATURES = {
         c_int, [c_void_p, c_int32, c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p]
     ),
     "dbgsom_hops": (c_int, [c_void_p, c_int32, c_void_p, c_int64, c_void_p]),
+    "dbgsom_sparse_code_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
+    "dbgsom_sparse_code": (
+        c_int,
+        [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
+         c_size_t, c_void_p],
+    ),
 }
 
 

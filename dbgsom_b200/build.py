@@ -10,8 +10,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libdbgsom_b200.so")
-SOURCES = ["capi.cu", "prep.cu", "bmu_simt.cu", "bmu_tc.cu", "bmu_resolve.cu", "accumulate.cu", "smooth.cu", "post.cu"]
-HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "dbgsom_b200.h")]
+SOURCES = ["capi.cu", "prep.cu", "bmu_simt.cu", "bmu_tc.cu", "bmu_resolve.cu", "accumulate.cu", "smooth.cu", "post.cu", "lars.cu"]
+HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "lars_core.cuh"), os.path.join(HERE, "..", "include", "dbgsom_b200.h")]
 
 
 def _nvcc() -> str:

@@ -17,6 +17,9 @@ int run_node_stats(const int32_t*, int, const double*, int, int64_t, const int32
 int run_label_hist(const int32_t*, int, const int32_t*, int64_t, int64_t, int, int, int32_t*, int64_t*, cudaStream_t);
 int run_umatrix(const double*, int, int, int64_t, const double*, double*, cudaStream_t);
 int run_hops(const int32_t*, int, uint16_t*, int64_t, cudaStream_t);
+size_t sparse_code_workspace_bytes(int64_t, int, int);
+int run_sparse_code(const double*, const double*, int64_t, int, int, int, int, const int32_t*, double*, int32_t*, void*,
+                    size_t, cudaStream_t);
 }  // namespace dbgsom
 
 using namespace dbgsom;
@@ -174,6 +177,20 @@ int dbgsom_hops(const int32_t* d_adj, int32_t M, uint16_t* d_hop, int64_t ldh, v
   if (!d_adj || !d_hop || M <= 0 || ldh < M) return DBGSOM_E_BADARG;
   if (!aligned16(d_adj)) return DBGSOM_E_UNSUPPORTED;
   return run_hops(d_adj, M, d_hop, ldh, as_stream(stream));
+}
+
+size_t dbgsom_sparse_code_workspace_bytes(int64_t n_threads, int32_t M, int32_t cholesky_capacity) {
+  return sparse_code_workspace_bytes(n_threads, M, cholesky_capacity);
+}
+
+int dbgsom_sparse_code(const double* d_gram, const double* d_cov, int64_t N, int32_t M, int32_t n_features,
+                       int32_t max_iter, int32_t cholesky_capacity, const int32_t* d_rows, double* d_code,
+                       int32_t* d_status, void* d_workspace, size_t workspace_bytes, void* stream) {
+  if (!d_gram || !d_cov || !d_code || !d_status || !d_workspace) return DBGSOM_E_BADARG;
+  if (N <= 0 || M <= 0 || n_features <= 0 || max_iter <= 0 || cholesky_capacity <= 0) return DBGSOM_E_BADARG;
+  if (workspace_bytes < sparse_code_workspace_bytes(128, M, cholesky_capacity)) return DBGSOM_E_WORKSPACE;
+  return run_sparse_code(d_gram, d_cov, N, M, n_features, max_iter, cholesky_capacity, d_rows, d_code, d_status,
+                         d_workspace, workspace_bytes, as_stream(stream));
 }
 
 }  // extern "C"

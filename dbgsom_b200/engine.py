@@ -741,6 +741,53 @@ class DeviceEngine:
             self._run_bmu(self.X, n, self.ldx, x16, self.W[0], self.M, n_bmu, True, idx, dist, backend=be)
             return dist.cpu().numpy(), idx.cpu().numpy().astype(np.int64)
 
+    # ------------------------------------------------------------------ sparse coding (transform)
+    def sparse_code(self, Xn: np.ndarray, Wn: np.ndarray, max_iter: int = 1000) -> np.ndarray:
+        """Non-negative LARS-lasso code of the row-normalised samples `Xn` [N, D] over the row-normalised
+        prototypes `Wn` [M, D] (what `SparseCoder(..., "lasso_lars", positive_code=True, transform_alpha=0)`
+        computes in dbgsom/BaseSom.py:241-268).  Gram matrix and correlations are two float64 GEMMs (cuBLAS
+        through torch), the per-sample paths run in `dbgsom_sparse_code`, one CUDA thread per sample."""
+        torch = self.torch
+        n, d = int(Xn.shape[0]), int(Xn.shape[1])
+        m = int(Wn.shape[0])
+        if Wn.shape[1] != d:
+            raise ValueError(f"X has {d} features, the map has {Wn.shape[1]}")
+        out = np.empty((n, m), dtype=np.float64)
+        with torch.cuda.device(self.dev):
+            W = torch.from_numpy(np.ascontiguousarray(Wn, dtype=np.float64)).to(self.dev)
+            gram = (W @ W.T).contiguous()
+            chunk = max(1024, min(n, int((1 << 30) // (8 * m))))  # cov + code of a chunk: 2 GiB at most
+            budget = 2 << 30  # scratch of the per-thread paths
+            for c0 in range(0, n, chunk):
+                c1 = min(n, c0 + chunk)
+                nc = c1 - c0
+                X = torch.from_numpy(np.ascontiguousarray(Xn[c0:c1])).to(self.dev).to(torch.float64)
+                cov = (X @ W.T).contiguous()
+                code = torch.zeros((nc, m), dtype=torch.float64, device=self.dev)
+                status = torch.zeros(nc, dtype=torch.int32, device=self.dev)
+                rows, n_rows = None, nc
+                for cap in (min(m, 32), min(m, 128), min(m, 1024)):
+                    per_thread = self.lib.dbgsom_sparse_code_workspace_bytes(1, m, cap)
+                    threads = max(128, min(-(-n_rows // 128) * 128, (budget // per_thread) // 128 * 128))
+                    ws = self._workspace("lars", self.lib.dbgsom_sparse_code_workspace_bytes(threads, m, cap))
+                    nat.check(
+                        self.lib.dbgsom_sparse_code(
+                            gram.data_ptr(), cov.data_ptr(), n_rows, m, d, int(max_iter), cap,
+                            rows.data_ptr() if rows is not None else None, code.data_ptr(), status.data_ptr(),
+                            ws.data_ptr(), ws.numel(), self._stream(),
+                        ),
+                        "dbgsom_sparse_code",
+                    )
+                    self.launches += 1
+                    rows = torch.nonzero(status & 1).to(torch.int32).view(-1).contiguous()
+                    n_rows = int(rows.numel())
+                    if n_rows == 0 or cap == m:
+                        break
+                if n_rows:
+                    raise nat.NativeError(f"{n_rows} samples need more than 1024 active atoms in the LARS path")
+                out[c0:c1] = code.cpu().numpy()
+        return out
+
     # ------------------------------------------------------------------ host-side reductions
     def allreduce_scalars(self, vals):
         if not (self.comm.enabled and self.comm.world > 1):

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define DBGSOM_ABI_VERSION 3
+#define DBGSOM_ABI_VERSION 4
 
 #define DBGSOM_OK 0
 #define DBGSOM_E_BADARG (-1)      /* null pointer, non-positive size, bad enum             */
@@ -294,6 +294,28 @@ int dbgsom_label_hist(const int32_t* d_idx, int32_t idx_stride, const int32_t* d
  */
 #define DBGSOM_HOPS_MAX_M 28000
 int dbgsom_hops(const int32_t* d_adj, int32_t M, uint16_t* d_hop, int64_t ldh, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * non-negative sparse coding
+ * replaces  the scikit-learn call of BaseSom.transform  dbgsom/BaseSom.py:241-268
+ *           SparseCoder(dictionary=normalize(W), positive_code=True, transform_alpha=0,
+ *                       transform_algorithm="lasso_lars").transform(normalize(X))
+ *           (also the first step of SomClassifier.predict_proba, dbgsom/SomClassifier.py:178-220)
+ * i.e. per sample scikit-learn 1.9's `_lars_path_solver` (Gram mode, method "lasso", positive, alpha_min 0,
+ * max_iter 1000), restated in csrc/lars_core.cuh; one CUDA thread per sample.
+ *   d_gram [M, M]  = Wn Wn^T  (Wn = row-normalised prototypes), d_cov [N, M] = Xn Wn^T, float64;
+ *   n_features = D (scales alpha like the reference); cholesky_capacity = largest active set the scratch is
+ *   sized for; d_rows = NULL or a list of N sample indices to process (rerun of the flagged ones);
+ *   d_code [N(all), M] float64 coefficients; d_status [N(all)] int32: bit 0 = the active set outgrew
+ *   cholesky_capacity (rerun with a larger one), bits 1-3 informational (early stop / degenerate regressor /
+ *   simultaneous sign changes, all handled as the reference does).
+ *   workspace: dbgsom_sparse_code_workspace_bytes(threads, M, cholesky_capacity); the call uses as many threads
+ *   (multiples of 128) as the workspace holds, so any size >= 128 threads' worth works.
+ */
+size_t dbgsom_sparse_code_workspace_bytes(int64_t n_threads, int32_t M, int32_t cholesky_capacity);
+int dbgsom_sparse_code(const double* d_gram, const double* d_cov, int64_t N, int32_t M, int32_t n_features,
+                       int32_t max_iter, int32_t cholesky_capacity, const int32_t* d_rows, double* d_code,
+                       int32_t* d_status, void* d_workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -112,6 +112,13 @@ class OracleEngine:
         (first,) = self.allreduce_arrays([first], op="min")
         return counts.reshape(m, n_classes), first.reshape(m, n_classes)
 
+    def sparse_code(self, Xn, Wn, max_iter=1000):
+        """The reference's own call (dbgsom/BaseSom.py:258-266) on the already normalised operands."""
+        from sklearn.decomposition import SparseCoder
+
+        coder = SparseCoder(dictionary=Wn, positive_code=True, transform_alpha=0, transform_algorithm="lasso_lars")
+        return coder.transform(Xn)
+
     def bmu_train(self, n_bmu, previous=False):
         return self.bmu(self.X, self.W_prev if previous else self.W, n_bmu)
 

@@ -115,3 +115,29 @@ def test_label_histogram_matches_numpy():
     np.minimum.at(exp_first, flat, np.arange(n, dtype=np.int64))
     np.testing.assert_array_equal(first.reshape(-1), exp_first)
     e.close()
+
+
+@pytest.mark.parametrize("case", ["sheet", "wide", "dense_paths"])
+def test_sparse_code_matches_sklearn(case):
+    """BaseSom.transform on the device (dbgsom_sparse_code) against the reference's scikit-learn call."""
+    from sklearn.decomposition import SparseCoder
+    from sklearn.preprocessing import normalize
+
+    rng = np.random.default_rng(11)
+    if case == "sheet":   # smooth trained-map-like dictionary: 2-7 active atoms per sample
+        u, v = np.meshgrid(np.linspace(0, 1, 9), np.linspace(0, 1, 9), indexing="ij")
+        feats = np.stack([u, v, np.sin(2 * u), np.cos(2 * v), u * v, np.ones_like(u)], axis=-1).reshape(-1, 6)
+        W = feats @ rng.normal(size=(6, 64)) + 0.05 * rng.normal(size=(81, 64))
+        X = W[rng.integers(0, 81, 6000)] + 0.3 * rng.normal(size=(6000, 64))
+    elif case == "wide":  # more atoms than features
+        W, X = rng.normal(size=(120, 24)) + 1.0, rng.normal(size=(3000, 24)) + 1.0
+    else:                 # long paths: active sets beyond the first Cholesky capacity (32) -> rerun at 128
+        W, X = rng.normal(size=(100, 96)), rng.normal(size=(700, 96))
+    Wn, Xn = normalize(W), normalize(X.astype(np.float32 if case == "wide" else np.float64))
+    ref = SparseCoder(dictionary=Wn, positive_code=True, transform_alpha=0, transform_algorithm="lasso_lars").transform(Xn)
+    e = engine()
+    code = e.sparse_code(Xn, Wn)
+    e.close()
+    if case == "dense_paths":
+        assert (np.count_nonzero(ref > 1e-12, axis=1) > 32).any()
+    np.testing.assert_allclose(code, ref, rtol=1e-6, atol=1e-9)

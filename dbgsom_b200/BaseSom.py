@@ -342,6 +342,11 @@ class BaseSom(BaseEstimator):
         Same result as dbgsom/BaseSom.py:241-268 (scikit-learn `SparseCoder`, `lasso_lars`, positive, alpha 0)
         computed on the device: the LARS-lasso path of every sample runs in `dbgsom_sparse_code`
         (csrc/lars_core.cuh restates scikit-learn's solver).
+
+        The path is evaluated in float64 for float64 and float32 samples alike.  For float32 samples
+        scikit-learn casts the Gram matrix to float32 and runs the Cholesky part of the path in float32
+        (`_sparse_encode`), so on ill-conditioned maps the reference's own codes carry float32 noise (up to
+        ~1e-3 on a smooth 400-neuron sheet); this implementation returns the float64 result there.
         """
         from sklearn.preprocessing import normalize
 

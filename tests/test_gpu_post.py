@@ -133,7 +133,7 @@ def test_sparse_code_matches_sklearn(case):
         W, X = rng.normal(size=(120, 24)) + 1.0, rng.normal(size=(3000, 24)) + 1.0
     else:                 # long paths: active sets beyond the first Cholesky capacity (32) -> rerun at 128
         W, X = rng.normal(size=(100, 96)), rng.normal(size=(700, 96))
-    Wn, Xn = normalize(W), normalize(X.astype(np.float32 if case == "wide" else np.float64))
+    Wn, Xn = normalize(W), normalize(X)
     ref = SparseCoder(dictionary=Wn, positive_code=True, transform_alpha=0, transform_algorithm="lasso_lars").transform(Xn)
     e = engine()
     code = e.sparse_code(Xn, Wn)
@@ -141,3 +141,20 @@ def test_sparse_code_matches_sklearn(case):
     if case == "dense_paths":
         assert (np.count_nonzero(ref > 1e-12, axis=1) > 32).any()
     np.testing.assert_allclose(code, ref, rtol=1e-6, atol=1e-9)
+
+
+def test_sparse_code_float32_samples():
+    """float32 samples: scikit-learn then runs the Cholesky part of the path in float32 (its Gram matrix is cast to
+    the dtype of X, sklearn/decomposition/_dict_learning.py `_sparse_encode`), the device path stays in float64.
+    On a well-conditioned dictionary both agree to float32 round-off."""
+    from sklearn.decomposition import SparseCoder
+    from sklearn.preprocessing import normalize
+
+    rng = np.random.default_rng(12)
+    W, X = rng.normal(size=(30, 64)), rng.normal(size=(2000, 64)).astype(np.float32)
+    Wn, Xn = normalize(W), normalize(X)
+    ref = SparseCoder(dictionary=Wn, positive_code=True, transform_alpha=0, transform_algorithm="lasso_lars").transform(Xn)
+    e = engine()
+    code = e.sparse_code(Xn, Wn)
+    e.close()
+    np.testing.assert_allclose(code, ref, rtol=0, atol=2e-6)

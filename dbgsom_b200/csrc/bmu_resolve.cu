@@ -130,7 +130,10 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) bmu_resolve_kernel(
 // per iteration against all R samples (R x RS_P accumulators in registers), so every shared-memory load
 // of a sample element feeds RS_P subtract/FMA pairs and every prototype element R of them: the float64
 // pipe is the limiter, not the load ports (the first version converted float -> double per use and was
-// bound by the conversion unit at ~20 % of the float64 rate).
+// bound by the conversion unit at ~20 % of the float64 rate).  The R x RS_P partial sums of the 32 lanes
+// are summed with one transposed butterfly (31 shuffle steps for 32 values; separate warp sums took 160
+// and were a third of the kernel's instructions); lane (r * RS_P + p) * 32 / (R * RS_P) then owns the
+// pair (sample r, prototype j0 + p) and keeps its own running top-2.
 constexpr int RS_P = 4;
 template <int NB, int R>
 __global__ void __launch_bounds__(256) bmu_rescan_kernel(const float* __restrict__ X, int64_t ldx, int D,
@@ -138,11 +141,16 @@ __global__ void __launch_bounds__(256) bmu_rescan_kernel(const float* __restrict
                                                         const int32_t* __restrict__ rescan_count,
                                                         const int32_t* __restrict__ rescan_rows, int want_dist,
                                                         int32_t* __restrict__ idx_out, double* __restrict__ dist_out) {
+  constexpr int V = R * RS_P;   // values per lane; 32 / V lanes end up holding each total
+  static_assert(V <= 32 && 32 % V == 0, "R * RS_P must divide the warp");
   extern __shared__ __align__(16) double xs[];  // [R][D]
-  __shared__ double m_d[8][R][2];
-  __shared__ int m_i[8][R][2];
+  __shared__ double m_d[8][V][2];
+  __shared__ int m_i[8][V][2];
   __shared__ int row_id[R];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int vi = lane / (32 / V);            // the (sample, prototype slot) pair this lane owns after the reduction
+  const int my_p = vi % RS_P;
+  const bool leader = lane % (32 / V) == 0;
   const int n = *rescan_count;
   const int groups = ceil_div(n, R);
   for (int g = blockIdx.x; g < groups; g += gridDim.x) {
@@ -158,15 +166,12 @@ __global__ void __launch_bounds__(256) bmu_rescan_kernel(const float* __restrict
       xs[e] = rid >= 0 ? (double)X[(int64_t)rid * ldx + d] : 0.0;
     }
     __syncthreads();
-    Top2 top[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) top[r].init();
+    Top2 mine;
+    mine.init();
     for (int j0 = warp * RS_P; j0 < M; j0 += 8 * RS_P) {
-      double acc[R][RS_P];
+      double acc[V];
 #pragma unroll
-      for (int r = 0; r < R; ++r)
-#pragma unroll
-        for (int p = 0; p < RS_P; ++p) acc[r][p] = 0.0;
+      for (int i = 0; i < V; ++i) acc[i] = 0.0;
       for (int d = lane * 2; d < D; d += 64) {  // D % 4 == 0: pairs never straddle the row end
         double2 w[RS_P];
 #pragma unroll
@@ -180,25 +185,17 @@ __global__ void __launch_bounds__(256) bmu_rescan_kernel(const float* __restrict
 #pragma unroll
           for (int p = 0; p < RS_P; ++p) {
             const double a = xv.x - w[p].x, b = xv.y - w[p].y;
-            acc[r][p] = fma(a, a, acc[r][p]);
-            acc[r][p] = fma(b, b, acc[r][p]);
+            acc[r * RS_P + p] = fma(a, a, acc[r * RS_P + p]);
+            acc[r * RS_P + p] = fma(b, b, acc[r * RS_P + p]);
           }
         }
       }
-#pragma unroll
-      for (int p = 0; p < RS_P; ++p) {
-        if (j0 + p < M) {  // warp-uniform
-#pragma unroll
-          for (int r = 0; r < R; ++r) top[r].offer(warp_sum(acc[r][p]), j0 + p);
-        }
-      }
+      const double tot = reduce_rows<V>(acc, lane);
+      if (leader && j0 + my_p < M) mine.offer(tot, j0 + my_p);
     }
-    if (lane == 0) {
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        m_d[warp][r][0] = top[r].d1; m_d[warp][r][1] = top[r].d2;
-        m_i[warp][r][0] = top[r].i1; m_i[warp][r][1] = top[r].i2;
-      }
+    if (leader) {
+      m_d[warp][vi][0] = mine.d1; m_d[warp][vi][1] = mine.d2;
+      m_i[warp][vi][0] = mine.i1; m_i[warp][vi][1] = mine.i2;
     }
     __syncthreads();
     if (threadIdx.x < R && row_id[threadIdx.x] >= 0) {
@@ -206,8 +203,10 @@ __global__ void __launch_bounds__(256) bmu_rescan_kernel(const float* __restrict
       Top2 t;
       t.init();
       for (int q = 0; q < 8; ++q) {
-        if (m_i[q][r][0] >= 0) t.offer(m_d[q][r][0], m_i[q][r][0]);
-        if (m_i[q][r][1] >= 0) t.offer(m_d[q][r][1], m_i[q][r][1]);
+        for (int p = 0; p < RS_P; ++p) {
+          if (m_i[q][r * RS_P + p][0] >= 0) t.offer(m_d[q][r * RS_P + p][0], m_i[q][r * RS_P + p][0]);
+          if (m_i[q][r * RS_P + p][1] >= 0) t.offer(m_d[q][r * RS_P + p][1], m_i[q][r * RS_P + p][1]);
+        }
       }
       const int64_t row = row_id[r];
       idx_out[row * NB] = t.i1;

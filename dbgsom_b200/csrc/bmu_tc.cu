@@ -186,41 +186,68 @@ __host__ __device__ constexpr uint32_t instr_desc_f16(int m, int n) {
   return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-// Keep the K smallest offered (score, prototype index) pairs of one row in a small shared-memory table;
-// `evicted` is the best score that did not fit (see RowTracker in common.cuh).  Equal scores are ordered
-// by prototype index, so among exact duplicates -- identical shadows give bit-identical scores -- the
-// lowest index always survives, which is the tie rule of the reference (sklearn/utils/_heap.pyx:46).
-// Rare, hence not inlined.
-template <int K>
-__device__ __noinline__ void table_offer(float s, int col, const int32_t* __restrict__ proto_of_col, int* tab_idx,
-                                         float* tab_val, int& n_app, float& evicted) {
-  const int j = proto_of_col[col];
-  if (n_app < K) {
-    tab_idx[n_app] = j;
-    tab_val[n_app] = s;
-  } else {
-    int worst = 0;
-    float wv = tab_val[0];
-    int wj = tab_idx[0];
+// Keep the KSUB = 4 smallest offered (score, prototype) pairs of one (row, epilogue warp) in shared memory:
+// four scores (one 16-byte word, +inf = free slot) and the four SHADOW COLUMNS they came from; the column ->
+// prototype translation (a global load) is left to the merge at the end of the row tile.  Returns
+// {gate, out}: gate = the largest score in the table afterwards (+inf while a slot is free) -- a later score
+// above the gate cannot enter, so the caller folds it (or the minimum of a whole chunk) into `evicted`
+// without calling; out = the score that left or did not fit (+inf if none).  Equal scores are ordered by
+// prototype index, so among exact duplicates -- identical shadows give bit-identical scores -- the lowest
+// index always survives, which is the tie rule of the reference (sklearn/utils/_heap.pyx:46); only that
+// rare case looks the indices up.  Not inlined (rare); everything it touches is shared memory or registers:
+// the first version took the prototype index from global memory and kept its counters on the stack, ~1000
+// cycles of latency per call, which on maps with many near-identical prototypes (17 M calls per million
+// rows late in a fit) stalled the epilogue behind the two accumulator buffers and tripled K1.
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ int4 lds_i4(uint32_t a) {
+  int4 v;
+  asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_f1(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_i1(uint32_t a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+__device__ __noinline__ float2 table_offer(float s, int col, const int32_t* __restrict__ proto_of_col, uint32_t val_addr,
+                                           uint32_t col_addr) {
+  const float kFree = __int_as_float(0x7f800000);
+  float4 v = lds_f4(val_addr);
+  int w = 0;
+  float wv = v.x;
+  if (v.y > wv) { wv = v.y; w = 1; }
+  if (v.z > wv) { wv = v.z; w = 2; }
+  if (v.w > wv) { wv = v.w; w = 3; }
+  float out = kFree;
+  bool replace = true;
+  if (wv != kFree) {
+    const int n_eq = (v.x == wv) + (v.y == wv) + (v.z == wv) + (v.w == wv);
+    if (s == wv || n_eq > 1) {  // rare: order equal scores by prototype index
+      const int4 c = lds_i4(col_addr);
+      const int cc[4] = {c.x, c.y, c.z, c.w};
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+      int wj = -1;
 #pragma unroll
-    for (int q = 1; q < K; ++q) {
-      const float v = tab_val[q];
-      const int jq = tab_idx[q];
-      if (v > wv || (v == wv && jq > wj)) {
-        wv = v;
-        wj = jq;
-        worst = q;
+      for (int q = 0; q < 4; ++q) {
+        if (vv[q] == wv) {
+          const int jq = proto_of_col[cc[q]];
+          if (jq > wj) { wj = jq; w = q; }
+        }
       }
-    }
-    if (s < wv || (s == wv && j < wj)) {
-      evicted = fminf(evicted, wv);
-      tab_idx[worst] = j;
-      tab_val[worst] = s;
+      replace = s < wv || (s == wv && proto_of_col[col] < wj);
     } else {
-      evicted = fminf(evicted, s);
+      replace = s < wv;
     }
+    out = replace ? wv : s;
   }
-  ++n_app;
+  if (replace) {
+    sts_f1(val_addr + 4 * w, s);
+    sts_i1(col_addr + 4 * w, col);
+    if (w == 0) v.x = s; else if (w == 1) v.y = s; else if (w == 2) v.z = s; else v.w = s;
+  }
+  return make_float2(fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)), out);
 }
 
 // ------------------------------------------------------------------------------------------ layout
@@ -482,8 +509,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const int sub = (warp - EPI_WARP0) >> 2;       // which of the four warps of this quarter
     const int t = quarter * 32 + lane;             // TMEM lane = row within the tile
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    int* my_idx = tab_idx + (t * EPI_SUBS + sub) * KSUB;
-    float* my_val = tab_val + (t * EPI_SUBS + sub) * KSUB;
+    static_assert(KSUB == 4, "table_offer handles four-entry tables");
+    const uint32_t my_col_addr = smem_u32(tab_idx + (t * EPI_SUBS + sub) * KSUB);  // shadow columns of my entries
+    const uint32_t my_val_addr = smem_u32(tab_val + (t * EPI_SUBS + sub) * KSUB);  // their scores
     constexpr int CHUNKS = BN / 32;
     constexpr float kInf = 3.0e38f;
     if (sub == 0) row_min[t] = kInf;
@@ -500,7 +528,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const int64_t row = tile_of(it) * BM + t;
       const float tau = row < N ? 2.f * tensor_score_bound(xnorm16[row], wmax, bound_coef) : 0.f;
       float m1 = kInf, m2 = kInf, thr = kInf, evicted = __int_as_float(0x7f800000);
-      int n_app = 0;
+      float gate = __int_as_float(0x7f800000);  // largest score in my table (+inf while a slot is free)
+      asm volatile("st.shared.v4.f32 [%0], {%1,%1,%1,%1};" ::"r"(my_val_addr), "f"(gate) : "memory");
       for (int nt = 0; nt < NT; ++nt) {
         mbar_wait(&bars->tmem_full[acc], acc_phase);
         tc_fence_after();
@@ -548,17 +577,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           }
           // pass B on the live registers: offer what is inside the bound (rare)
           if (a1 <= thr) {
+            if (a1 > gate) {
+              // the table is full and nothing in this chunk beats its worst entry: the chunk's in-bound scores
+              // are all evicted, and the smallest of them is a1
+              evicted = fminf(evicted, a1);
+            } else {
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const float s0 = fmaf(-2.f, __uint_as_float(r[4 * g + 0]), w4[g].x);
-              const float s1 = fmaf(-2.f, __uint_as_float(r[4 * g + 1]), w4[g].y);
-              const float s2 = fmaf(-2.f, __uint_as_float(r[4 * g + 2]), w4[g].z);
-              const float s3 = fmaf(-2.f, __uint_as_float(r[4 * g + 3]), w4[g].w);
-              if (fminf(fminf(s0, s1), fminf(s2, s3)) <= thr) {
-                if (s0 <= thr) table_offer<KSUB>(s0, col + 4 * g + 0, proto_of_col, my_idx, my_val, n_app, evicted);
-                if (s1 <= thr) table_offer<KSUB>(s1, col + 4 * g + 1, proto_of_col, my_idx, my_val, n_app, evicted);
-                if (s2 <= thr) table_offer<KSUB>(s2, col + 4 * g + 2, proto_of_col, my_idx, my_val, n_app, evicted);
-                if (s3 <= thr) table_offer<KSUB>(s3, col + 4 * g + 3, proto_of_col, my_idx, my_val, n_app, evicted);
+              for (int g = 0; g < 8; ++g) {
+                const float s0 = fmaf(-2.f, __uint_as_float(r[4 * g + 0]), w4[g].x);
+                const float s1 = fmaf(-2.f, __uint_as_float(r[4 * g + 1]), w4[g].y);
+                const float s2 = fmaf(-2.f, __uint_as_float(r[4 * g + 2]), w4[g].z);
+                const float s3 = fmaf(-2.f, __uint_as_float(r[4 * g + 3]), w4[g].w);
+                if (fminf(fminf(s0, s1), fminf(s2, s3)) <= thr) {
+                  const float sq[4] = {s0, s1, s2, s3};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    if (sq[e] <= thr) {
+                      if (sq[e] > gate) {
+                        evicted = fminf(evicted, sq[e]);
+                      } else {
+                        const float2 o = table_offer(sq[e], col + 4 * g + e, proto_of_col, my_val_addr, my_col_addr);
+                        gate = o.x;
+                        evicted = fminf(evicted, o.y);
+                      }
+                    }
+                  }
+                }
               }
             }
           }
@@ -571,7 +615,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
       }
       // merge the four trackers of each row
-      sub_state[t * EPI_SUBS + sub] = make_float4(m1, m2, evicted, __int_as_float(n_app));
+      sub_state[t * EPI_SUBS + sub] = make_float4(m1, m2, evicted, 0.f);
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
       if (sub == 0) {
         float g1 = kInf, g2 = kInf, ev = __int_as_float(0x7f800000);
@@ -590,11 +634,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         bool overflow = ev <= gthr;
 #pragma unroll 1
         for (int q = 0; q < EPI_SUBS; ++q) {
-          const int have = min(__float_as_int(sub_state[t * EPI_SUBS + q].w), KSUB);
-          for (int e = 0; e < have; ++e) {
+          for (int e = 0; e < KSUB; ++e) {
             const float v = tab_val[(t * EPI_SUBS + q) * KSUB + e];
-            if (v <= gthr) {
-              const int jj = tab_idx[(t * EPI_SUBS + q) * KSUB + e];
+            if (v <= gthr) {  // free slots hold +inf, gthr is finite
+              const int jj = proto_of_col[tab_idx[(t * EPI_SUBS + q) * KSUB + e]];
               if (cnt < kMaxCand) out[cnt] = jj;
               ++cnt;
               if (v < bv || (v == bv && jj < best)) {

@@ -13,7 +13,7 @@ _LIB = None
 LIB_NAME = "libdbgsom_b200.so"
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_CAND = 8
 BMU_SIMT = 0
 BMU_TENSOR = 1
@@ -44,6 +44,8 @@ class BmuArgs(C.Structure):
         ("scale", c_float),
         ("M", c_int32),
         ("Mpad", c_int32),
+        ("proto_stride", c_int32),
+        ("ties_any", c_int32),
         ("n_bmu", c_int32),
         ("backend", c_int32),
         ("n_pass", c_int32),
@@ -113,6 +115,7 @@ SIGNATURES = {
         [c_void_p, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p,
          c_void_p, c_void_p, c_void_p, c_void_p],
     ),
+    "dbgsom_exclude_duplicates": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dbgsom_bmu_workspace_bytes": (c_size_t, [c_int64, c_int32]),
     "dbgsom_bmu": (c_int, [C.POINTER(BmuArgs), c_void_p]),
     "dbgsom_bmu_candidates": (c_int, [C.POINTER(BmuArgs), c_void_p]),

@@ -186,18 +186,18 @@ __host__ __device__ constexpr uint32_t instr_desc_f16(int m, int n) {
   return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-// Keep the KSUB = 4 smallest offered (score, prototype) pairs of one (row, epilogue warp) in shared memory:
-// four scores (one 16-byte word, +inf = free slot) and the four SHADOW COLUMNS they came from; the column ->
-// prototype translation (a global load) is left to the merge at the end of the row tile.  Returns
-// {gate, out}: gate = the largest score in the table afterwards (+inf while a slot is free) -- a later score
-// above the gate cannot enter, so the caller folds it (or the minimum of a whole chunk) into `evicted`
-// without calling; out = the score that left or did not fit (+inf if none).  Equal scores are ordered by
-// prototype index, so among exact duplicates -- identical shadows give bit-identical scores -- the lowest
-// index always survives, which is the tie rule of the reference (sklearn/utils/_heap.pyx:46); only that
-// rare case looks the indices up.  Not inlined (rare); everything it touches is shared memory or registers:
-// the first version took the prototype index from global memory and kept its counters on the stack, ~1000
-// cycles of latency per call, which on maps with many near-identical prototypes (17 M calls per million
-// rows late in a fit) stalled the epilogue behind the two accumulator buffers and tripled K1.
+// Keep the KSUB = 4 smallest offered (score, prototype index) pairs of one (row, epilogue warp) in shared
+// memory: four scores (one 16-byte word; +inf = free slot) and their four prototype indices (INT_MAX for a
+// free slot).  Pairs are ordered by score, then by prototype index, so among exact duplicates -- identical
+// shadows give bit-identical scores -- the lowest index always survives, which is the tie rule of the
+// reference (sklearn/utils/_heap.pyx:46).  Returns {gate score, gate index, out}: the gate is the largest
+// pair in the table afterwards -- a later pair above it cannot enter, so the caller folds such a score (or
+// the minimum of a whole chunk) into `evicted` without calling; out = the score that left or did not fit
+// (+inf if none).  Not inlined (rare); everything it touches is shared memory or registers: the first
+// version looked the prototype index up in global memory and kept its counters on the stack, ~1000 cycles
+// of latency per call, which on maps with many near-identical prototypes (17 M calls per million rows late
+// in a fit, most of them exact score ties) stalled the epilogue behind the two accumulator buffers and
+// tripled K1.
 __device__ __forceinline__ float4 lds_f4(uint32_t a) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
@@ -210,44 +210,56 @@ __device__ __forceinline__ int4 lds_i4(uint32_t a) {
 }
 __device__ __forceinline__ void sts_f1(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 __device__ __forceinline__ void sts_i1(uint32_t a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ bool pair_after(float va, int ja, float vb, int jb) {  // (va, ja) > (vb, jb)
+  return va > vb || (va == vb && ja > jb);
+}
 
-__device__ __noinline__ float2 table_offer(float s, int col, const int32_t* __restrict__ proto_of_col, uint32_t val_addr,
-                                           uint32_t col_addr) {
-  const float kFree = __int_as_float(0x7f800000);
-  float4 v = lds_f4(val_addr);
-  int w = 0;
-  float wv = v.x;
-  if (v.y > wv) { wv = v.y; w = 1; }
-  if (v.z > wv) { wv = v.z; w = 2; }
-  if (v.w > wv) { wv = v.w; w = 3; }
-  float out = kFree;
-  bool replace = true;
-  if (wv != kFree) {
-    const int n_eq = (v.x == wv) + (v.y == wv) + (v.z == wv) + (v.w == wv);
-    if (s == wv || n_eq > 1) {  // rare: order equal scores by prototype index
-      const int4 c = lds_i4(col_addr);
-      const int cc[4] = {c.x, c.y, c.z, c.w};
-      const float vv[4] = {v.x, v.y, v.z, v.w};
-      int wj = -1;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (vv[q] == wv) {
-          const int jq = proto_of_col[cc[q]];
-          if (jq > wj) { wj = jq; w = q; }
-        }
-      }
-      replace = s < wv || (s == wv && proto_of_col[col] < wj);
-    } else {
-      replace = s < wv;
-    }
-    out = replace ? wv : s;
+// Per-CTA constants of the epilogue, kept in shared memory so that slow_offer needs few arguments.
+struct EpiConst {
+  const int32_t* proto_of_col;
+  uint32_t pstride, mpad;
+  int any_order;
+};
+constexpr uint32_t kTabIdxOffset = 128 * 4 * 4 * 4;  // BM * EPI_SUBS * KSUB * 4: scores -> indices of the same table
+
+// Offer (s, shadow column) to the table at val_addr.  Returns {fast gate, out}: `out` is the score that left
+// the table or did not fit (+inf if none); the FAST GATE g lets the caller skip the call: a later score >= g
+// cannot enter.  With any_order (equal scores need no index order, see dbgsom_exclude_duplicates) g is the
+// largest score in the table, otherwise the next float above it, so that an exact tie still comes here and is
+// decided by the prototype index.  +inf while a slot is free.
+__device__ __noinline__ float2 slow_offer(float s, int col, uint32_t val_addr, uint32_t const_addr) {
+  const EpiConst* ec;
+  {
+    uint64_t g;
+    asm volatile("cvta.shared.u64 %0, %1;" : "=l"(g) : "l"((uint64_t)const_addr));
+    ec = reinterpret_cast<const EpiConst*>(g);
   }
+  const uint32_t idx_addr = val_addr + kTabIdxOffset;
+  const int j = ec->pstride ? (int)(((uint32_t)col * ec->pstride) % ec->mpad) : ec->proto_of_col[col];
+  const float4 v4 = lds_f4(val_addr);
+  const int4 j4 = lds_i4(idx_addr);
+  float v0 = v4.x, v1 = v4.y, v2 = v4.z, v3 = v4.w;
+  int c0 = j4.x, c1 = j4.y, c2 = j4.z, c3 = j4.w;
+  // largest pair of the table (scalars only: indexed local arrays would live in local memory)
+  int w = 0;
+  float wv = v0;
+  int wc = c0;
+  if (pair_after(v1, c1, wv, wc)) { w = 1; wv = v1; wc = c1; }
+  if (pair_after(v2, c2, wv, wc)) { w = 2; wv = v2; wc = c2; }
+  if (pair_after(v3, c3, wv, wc)) { w = 3; wv = v3; wc = c3; }
+  const bool replace = pair_after(wv, wc, s, j);
+  const float out = replace ? wv : s;  // +inf when a free slot was taken: a no-op for the caller's minimum
   if (replace) {
     sts_f1(val_addr + 4 * w, s);
-    sts_i1(col_addr + 4 * w, col);
-    if (w == 0) v.x = s; else if (w == 1) v.y = s; else if (w == 2) v.z = s; else v.w = s;
+    sts_i1(idx_addr + 4 * w, j);
+    if (w == 0) v0 = s;
+    if (w == 1) v1 = s;
+    if (w == 2) v2 = s;
+    if (w == 3) v3 = s;
   }
-  return make_float2(fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)), out);
+  float g = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
+  if (!ec->any_order && g < 3.0e38f) g = nextafterf(g, __int_as_float(0x7f800000));
+  return make_float2(g, out);
 }
 
 // ------------------------------------------------------------------------------------------ layout
@@ -287,6 +299,7 @@ struct Barriers {
   uint64_t a_full, a_empty;
   uint64_t tmem_full[4], tmem_empty[4];
   uint32_t tmem_base;
+  EpiConst epi;
 };
 
 // CL: thread-block cluster size (1, 2 or 4).  The CTAs of a cluster work on different row tiles in lock
@@ -300,7 +313,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     bmu_cand_tensor_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                            const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
                            int64_t N, int KB, int NT, const float* __restrict__ wnorm,
-                           const int32_t* __restrict__ proto_of_col, const float* __restrict__ xnorm16,
+                           const int32_t* __restrict__ proto_of_col, int pstride, int ties_any,
+                           const float* __restrict__ xnorm16,
                            const float* __restrict__ wmax, float bound_coef,
                            int32_t* __restrict__ idx_out, int32_t* __restrict__ cand_idx,
                            uint8_t* __restrict__ cand_count) {
@@ -315,8 +329,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   uint8_t* stages = smem + C::RES_BYTES;               // ring
   uint8_t* ring = stages + C::STAGES * C::STAGE_BYTES;  // candidate tables
   Barriers* bars = reinterpret_cast<Barriers*>(ring + C::RING_BYTES);
-  int* tab_idx = reinterpret_cast<int*>(ring);
-  float* tab_val = reinterpret_cast<float*>(ring + BM * EPI_SUBS * KSUB * 4);
+  float* tab_val = reinterpret_cast<float*>(ring);
+  int* tab_idx = reinterpret_cast<int*>(ring + BM * EPI_SUBS * KSUB * 4);  // = tab_val + kTabIdxOffset bytes
   float* row_min = reinterpret_cast<float*>(ring + BM * EPI_SUBS * KSUB * 8);
   float4* sub_state = reinterpret_cast<float4*>(ring + BM * EPI_SUBS * KSUB * 8 + BM * 4);
   float* wn_smem = reinterpret_cast<float*>(ring + C::RING_BYTES + C::MISC_BYTES);
@@ -509,9 +523,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const int sub = (warp - EPI_WARP0) >> 2;       // which of the four warps of this quarter
     const int t = quarter * 32 + lane;             // TMEM lane = row within the tile
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    static_assert(KSUB == 4, "table_offer handles four-entry tables");
-    const uint32_t my_col_addr = smem_u32(tab_idx + (t * EPI_SUBS + sub) * KSUB);  // shadow columns of my entries
-    const uint32_t my_val_addr = smem_u32(tab_val + (t * EPI_SUBS + sub) * KSUB);  // their scores
+    static_assert(KSUB == 4 && BM * EPI_SUBS * KSUB * 4 == kTabIdxOffset, "slow_offer handles four-entry tables");
+    const uint32_t my_val_addr = smem_u32(tab_val + (t * EPI_SUBS + sub) * KSUB);  // scores of my entries
+    const uint32_t my_idx_addr = my_val_addr + kTabIdxOffset;                      // their prototype indices
+    // equal scores need no index order when exact copies have left the search (dbgsom_exclude_duplicates)
+    const bool any_order = NB == 1 && ties_any != 0;
+    if (threadIdx.x == EPI_WARP0 * 32) {
+      bars->epi.proto_of_col = proto_of_col;
+      bars->epi.pstride = (uint32_t)pstride;
+      bars->epi.mpad = (uint32_t)(NT * BN);
+      bars->epi.any_order = any_order ? 1 : 0;
+    }
+    const uint32_t epi_const_addr = smem_u32(&bars->epi);
     constexpr int CHUNKS = BN / 32;
     constexpr float kInf = 3.0e38f;
     if (sub == 0) row_min[t] = kInf;
@@ -528,8 +551,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const int64_t row = tile_of(it) * BM + t;
       const float tau = row < N ? 2.f * tensor_score_bound(xnorm16[row], wmax, bound_coef) : 0.f;
       float m1 = kInf, m2 = kInf, thr = kInf, evicted = __int_as_float(0x7f800000);
-      float gate = __int_as_float(0x7f800000);  // largest score in my table (+inf while a slot is free)
+      float gate = __int_as_float(0x7f800000);  // fast gate of my table (see slow_offer); +inf while a slot is free
       asm volatile("st.shared.v4.f32 [%0], {%1,%1,%1,%1};" ::"r"(my_val_addr), "f"(gate) : "memory");
+      asm volatile("st.shared.v4.s32 [%0], {%1,%1,%1,%1};" ::"r"(my_idx_addr), "r"(0x7fffffff) : "memory");
       for (int nt = 0; nt < NT; ++nt) {
         mbar_wait(&bars->tmem_full[acc], acc_phase);
         tc_fence_after();
@@ -575,32 +599,62 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             m1 = fminf(m1, a1);
             thr = m2 < 1.0e38f ? m2 + tau : kInf;
           }
-          // pass B on the live registers: offer what is inside the bound (rare)
+          // pass B on the live registers: offer what is inside the bound.  A score at or above the fast gate
+          // cannot enter the table and only lowers `evicted`; the rest goes through slow_offer (one out-of-line
+          // copy: the 16 epilogue warps share the instruction cache).  Three cases, cheapest first:
+          //  * the whole chunk is at or above the gate (rows with thousands of near-identical prototypes inside
+          //    their bound, once the table is full): one minimum;
+          //  * exactly one score is in bound -- the chunk minimum itself, the usual "new running minimum" event:
+          //    one call, made by all such lanes of the warp together;
+          //  * several: the scores are parked in local memory so that a loop can index them, lanes advancing
+          //    through their own in-bound scores in parallel.
           if (a1 <= thr) {
-            if (a1 > gate) {
-              // the table is full and nothing in this chunk beats its worst entry: the chunk's in-bound scores
-              // are all evicted, and the smallest of them is a1
+            if (a1 >= gate) {
               evicted = fminf(evicted, a1);
             } else {
+              uint32_t inb = 0;
 #pragma unroll
               for (int g = 0; g < 8; ++g) {
-                const float s0 = fmaf(-2.f, __uint_as_float(r[4 * g + 0]), w4[g].x);
-                const float s1 = fmaf(-2.f, __uint_as_float(r[4 * g + 1]), w4[g].y);
-                const float s2 = fmaf(-2.f, __uint_as_float(r[4 * g + 2]), w4[g].z);
-                const float s3 = fmaf(-2.f, __uint_as_float(r[4 * g + 3]), w4[g].w);
-                if (fminf(fminf(s0, s1), fminf(s2, s3)) <= thr) {
-                  const float sq[4] = {s0, s1, s2, s3};
+                inb |= (fmaf(-2.f, __uint_as_float(r[4 * g + 0]), w4[g].x) <= thr ? 1u : 0u) << (4 * g + 0);
+                inb |= (fmaf(-2.f, __uint_as_float(r[4 * g + 1]), w4[g].y) <= thr ? 1u : 0u) << (4 * g + 1);
+                inb |= (fmaf(-2.f, __uint_as_float(r[4 * g + 2]), w4[g].z) <= thr ? 1u : 0u) << (4 * g + 2);
+                inb |= (fmaf(-2.f, __uint_as_float(r[4 * g + 3]), w4[g].w) <= thr ? 1u : 0u) << (4 * g + 3);
+              }
+              if ((inb & (inb - 1)) == 0) {
+                if (inb) {
+                  const float2 o = slow_offer(a1, col + __ffs(inb) - 1, my_val_addr, epi_const_addr);
+                  gate = o.x;
+                  evicted = fminf(evicted, o.y);
+                }
+              } else {
+                float sc[32];
+                uint32_t need = 0;
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                  sc[4 * g + 0] = fmaf(-2.f, __uint_as_float(r[4 * g + 0]), w4[g].x);
+                  sc[4 * g + 1] = fmaf(-2.f, __uint_as_float(r[4 * g + 1]), w4[g].y);
+                  sc[4 * g + 2] = fmaf(-2.f, __uint_as_float(r[4 * g + 2]), w4[g].z);
+                  sc[4 * g + 3] = fmaf(-2.f, __uint_as_float(r[4 * g + 3]), w4[g].w);
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
-                    if (sq[e] <= thr) {
-                      if (sq[e] > gate) {
-                        evicted = fminf(evicted, sq[e]);
-                      } else {
-                        const float2 o = table_offer(sq[e], col + 4 * g + e, proto_of_col, my_val_addr, my_col_addr);
-                        gate = o.x;
-                        evicted = fminf(evicted, o.y);
-                      }
-                    }
+                    // in bound but not below the gate as it stands (it only falls): evicted, branch-free
+                    const float se = sc[4 * g + e];
+                    const bool in = se <= thr, out = se >= gate;
+                    evicted = fminf(evicted, in && out ? se : __int_as_float(0x7f800000));
+                    need |= (in && !out ? 1u : 0u) << (4 * g + e);
+                  }
+                }
+#pragma unroll 1
+                while (need) {
+                  const int e = __ffs(need) - 1;
+                  need &= need - 1;
+                  const float se = sc[e];
+                  if (se >= gate) {
+                    evicted = fminf(evicted, se);
+                  } else {
+                    const float2 o = slow_offer(se, col + e, my_val_addr, epi_const_addr);
+                    gate = o.x;
+                    evicted = fminf(evicted, o.y);
                   }
                 }
               }
@@ -637,7 +691,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           for (int e = 0; e < KSUB; ++e) {
             const float v = tab_val[(t * EPI_SUBS + q) * KSUB + e];
             if (v <= gthr) {  // free slots hold +inf, gthr is finite
-              const int jj = proto_of_col[tab_idx[(t * EPI_SUBS + q) * KSUB + e]];
+              const int jj = tab_idx[(t * EPI_SUBS + q) * KSUB + e];
               if (cnt < kMaxCand) out[cnt] = jj;
               ++cnt;
               if (v < bv || (v == bv && jj < best)) {
@@ -770,8 +824,10 @@ int launch_cfg_cl(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t
   if (grid > max_grid) grid = max_grid;
   cfg.gridDim = dim3((unsigned)grid);
   const float coef = tensor_bound_coef(NPASS, a.bound_scale);
-  DBGSOM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, mxh, mxl, mwh, mwl, a.N, KB, NT, a.d_wnorm, a.d_proto_of_col,
-                                     a.d_xnorm16, a.d_wmax, coef, a.d_idx, ws.cand_idx, ws.cand_count));
+  // the arithmetic form needs c * stride < 2^32 for every shadow row c
+  const int pstride = a.proto_stride > 0 && a.Mpad <= 65535 && a.proto_stride < a.Mpad ? a.proto_stride : 0;
+  DBGSOM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, mxh, mxl, mwh, mwl, a.N, KB, NT, a.d_wnorm, a.d_proto_of_col, pstride,
+                                     a.n_bmu == 1 ? a.ties_any : 0, a.d_xnorm16, a.d_wmax, coef, a.d_idx, ws.cand_idx, ws.cand_count));
   DBGSOM_LAUNCH_CHECK();
   return DBGSOM_OK;
 }

@@ -168,6 +168,67 @@ __global__ void __launch_bounds__(128) prepare_w_kernel(const double* __restrict
   }
 }
 
+// ------------------------------------------------------------------------------------------ duplicates
+// Exact copies among the prototypes.  The reference breaks exact distance ties by the lowest index
+// (sklearn/utils/_heap.pyx:46), so a prototype that equals a LOWER-indexed one element by element can never be
+// the answer of a top-1 search: its wnorm is set to +inf, which takes it out of the tensor candidate search.
+// With the copies gone, equal approximate scores no longer need to be ordered by prototype index in the
+// epilogue (bmu_tc.cu, args.ties_any) -- on collapsed maps that ordering was most of its work.
+// Step 1: an order-independent 64-bit hash of every row (values, so that -0.0 == +0.0 hash alike).
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {  // splitmix64 finaliser
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return z ^ (z >> 31);
+}
+__global__ void __launch_bounds__(128) row_hash_kernel(const double* __restrict__ W, int M, int D,
+                                                      unsigned long long* __restrict__ hash) {
+  __shared__ unsigned long long part[4];
+  const int j = blockIdx.x;
+  unsigned long long h = 0;
+  for (int d = threadIdx.x; d < D; d += 128) {
+    const double w = W[(int64_t)j * D + d] + 0.0;  // -0.0 -> +0.0
+    h += mix64((uint64_t)__double_as_longlong(w) + 0x9e3779b97f4a7c15ull * (uint64_t)(d + 1));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(kFullMask, h, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = h;
+  __syncthreads();
+  if (threadIdx.x == 0) hash[j] = part[0] + part[1] + part[2] + part[3];
+}
+// Step 2: one thread per prototype j looks for an equal hash among the lower indices -- tiles of 256 hashes
+// staged in shared memory, compared branch-free -- and confirms a hit element by element (lowest index first).
+__global__ void __launch_bounds__(256) mark_duplicates_kernel(const double* __restrict__ W, int M, int D,
+                                                             const unsigned long long* __restrict__ hash,
+                                                             const int32_t* __restrict__ col_of_proto,
+                                                             float* __restrict__ wnorm) {
+  __shared__ unsigned long long tile[256];
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  const unsigned long long hj = j < M ? hash[j] : 0ull;
+  bool done = j >= M;
+  for (int t = 0; t <= (int)blockIdx.x; ++t) {  // block-uniform trip count
+    __syncthreads();
+    const int src = t * 256 + threadIdx.x;
+    tile[threadIdx.x] = src < M ? hash[src] : 0ull;
+    __syncthreads();
+    if (done) continue;
+    const int lim = min(256, j - t * 256);  // only lower indices
+    bool hit = false;
+#pragma unroll 16
+    for (int q = 0; q < 256; ++q) hit |= (tile[q] == hj) & (q < lim);
+    if (!hit) continue;
+    for (int q = 0; q < lim && !done; ++q) {
+      if (tile[q] != hj) continue;
+      const int p = t * 256 + q;
+      bool same = true;
+      for (int d = 0; d < D && same; ++d) same = W[(int64_t)p * D + d] == W[(int64_t)j * D + d];
+      if (same) {
+        wnorm[col_of_proto ? col_of_proto[j] : j] = __int_as_float(0x7f800000);
+        done = true;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ rows
 // Sequential prototype-row arithmetic of the growth step (dbgsom/BaseSom.py:641-644, :705-726,
 // :824-827, :835-837): one CTA, ops in list order, a block barrier between ops.
@@ -227,6 +288,15 @@ int run_prepare_w(const double* W, int M, int D, const float* shift, float scale
   prepare_w_kernel<<<rows, 128, 0, s>>>(W, M, D, shift, wshift, scale, W32, reinterpret_cast<__half*>(W16_hi),
                                         reinterpret_cast<__half*>(W16_lo), ld16, W16_hi ? col_of_proto : nullptr, wnorm,
                                         wmax);
+  DBGSOM_LAUNCH_CHECK();
+  return DBGSOM_OK;
+}
+
+int run_exclude_duplicates(const double* W, int M, int D, const int32_t* col_of_proto, float* wnorm,
+                           unsigned long long* hash, cudaStream_t s) {
+  row_hash_kernel<<<M, 128, 0, s>>>(W, M, D, hash);
+  DBGSOM_LAUNCH_CHECK();
+  mark_duplicates_kernel<<<ceil_div(M, 256), 256, 0, s>>>(W, M, D, hash, col_of_proto, wnorm);
   DBGSOM_LAUNCH_CHECK();
   return DBGSOM_OK;
 }

@@ -385,13 +385,24 @@ class DeviceEngine:
         big = m >= 128 and n * m * self.ldx >= (1 << 31)
         return (nat.BMU_TENSOR, 3) if big else (nat.BMU_SIMT, 0)
 
-    def _prepare_w(self, W, m: int, tensor: bool, need_lo: bool) -> int:
+    def _prepare_w(self, W, m: int, tensor: bool, need_lo: bool, top1: bool = True) -> int:
         torch = self.torch
         mpad = _round_up(m, 256)
         if tensor:
             if getattr(self, "_perm_mpad", None) != mpad:
-                # fixed pseudo-random visiting order of the shadow rows (see bmu_tc.cu)
-                proto_of_col = np.random.default_rng(0x5EED + mpad).permutation(mpad).astype(np.int32)
+                # fixed scattered visiting order of the shadow rows (see bmu_tc.cu): shadow row c holds
+                # prototype (c * stride) % mpad, stride ~ mpad / golden ratio and coprime to mpad -- a
+                # low-discrepancy sequence over the map that the kernel can evaluate in registers
+                stride = int(round(mpad * 0.6180339887498949)) | 1
+                while math.gcd(stride, mpad) != 1:
+                    stride += 2
+                self.proto_stride = stride if mpad <= 65535 else 0
+                proto_of_col = ((np.arange(mpad, dtype=np.int64) * stride) % mpad).astype(np.int32)
+                if os.environ.get("DBGSOM_PERM") == "random":  # tuning switch
+                    proto_of_col = np.random.default_rng(0x5EED + mpad).permutation(mpad).astype(np.int32)
+                    self.proto_stride = 0
+                if os.environ.get("DBGSOM_PERM") == "table":
+                    self.proto_stride = 0
                 col_of_proto = np.empty_like(proto_of_col)
                 col_of_proto[proto_of_col] = np.arange(mpad, dtype=np.int32)
                 self.proto_of_col = torch.from_numpy(proto_of_col).to(self.dev)
@@ -414,6 +425,20 @@ class DeviceEngine:
             "dbgsom_prepare_w",
         )
         self.launches += 3 if tensor else 2
+        # top-1 searches: exact copies of a lower-indexed prototype can never win (lowest index takes exact
+        # ties), so they leave the candidate search and the epilogue need not order equal scores
+        self._ties_any = bool(tensor and top1)
+        if self._ties_any:
+            if getattr(self, "_row_hash", None) is None or self._row_hash.numel() < m:
+                self._row_hash = torch.empty(max(m, self.cap), dtype=torch.int64, device=self.dev)
+            nat.check(
+                self.lib.dbgsom_exclude_duplicates(
+                    W.data_ptr(), m, self.ldx, self.col_of_proto.data_ptr(), self.wnorm.data_ptr(),
+                    self._row_hash.data_ptr(), self._stream(),
+                ),
+                "dbgsom_exclude_duplicates",
+            )
+            self.launches += 2
         return mpad
 
     def _run_bmu(self, X, n: int, ldx: int, x16, W, m: int, n_bmu: int, want_dist: bool, idx, dist, backend=None):
@@ -422,7 +447,7 @@ class DeviceEngine:
         if W.shape[0] > self.W32.shape[0]:
             self.W32 = self.torch.zeros((W.shape[0], self.ldx), dtype=self.torch.float32, device=self.dev)
         with self._Phase(self, "prepare_w"):
-            mpad = self._prepare_w(W, m, be == nat.BMU_TENSOR, n_pass == 3)
+            mpad = self._prepare_w(W, m, be == nat.BMU_TENSOR, n_pass == 3, top1=n_bmu == 1)
         self._bmu_search(X, n, ldx, x16, W, m, mpad, n_bmu, want_dist, idx, dist, (be, n_pass))
 
     def _bmu_search(self, X, n, ldx, x16, W, m, mpad, n_bmu, want_dist, idx, dist, backend, ws_key="bmu"):
@@ -440,6 +465,8 @@ class DeviceEngine:
             a.d_W16_lo = self.W16_lo.data_ptr() if self.W16_lo is not None else None
             a.d_wnorm = self.wnorm.data_ptr()
             a.d_proto_of_col = self.proto_of_col.data_ptr()
+            a.proto_stride = self.proto_stride
+            a.ties_any = int(self._ties_any and n_bmu == 1)
         a.d_W, a.d_W32, a.d_wmax = W.data_ptr(), self.W32.data_ptr(), self.wmax.data_ptr()
         a.scale, a.M, a.Mpad, a.n_bmu = self.scale, m, mpad, n_bmu
         a.backend, a.n_pass, a.bound_scale, a.tie_rel = be, n_pass, self.bound_scale, 0.0

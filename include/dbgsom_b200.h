@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define DBGSOM_ABI_VERSION 4
+#define DBGSOM_ABI_VERSION 5
 
 #define DBGSOM_OK 0
 #define DBGSOM_E_BADARG (-1)      /* null pointer, non-positive size, bad enum             */
@@ -101,6 +101,16 @@ int dbgsom_prepare_w(const double* d_W, int M, int D, const float* d_shift, floa
                      const int32_t* d_col_of_proto /*[Mpad] or NULL*/, float* d_wnorm /*[Mpad]*/,
                      double* d_wshift /*[D]*/, float* d_wmax /*[4]*/, void* stream);
 
+/* Optional, after dbgsom_prepare_w and before a top-1 (n_bmu = 1) tensor search: sets wnorm to +inf for every
+ * prototype that equals a LOWER-indexed prototype element by element.  The reference gives exact distance ties
+ * to the lowest index (sklearn/utils/_heap.pyx:46), so such a copy can never be the answer of a top-1 search;
+ * with the copies out of the search the epilogue may keep equally scored prototypes in any order
+ * (dbgsom_bmu_args.ties_any = 1), which removes most of its work on collapsed maps (thousands of near-identical
+ * prototypes).  Do not use it for n_bmu = 2, where a copy is the legitimate second winner.
+ * d_hash: scratch, M 64-bit words. */
+int dbgsom_exclude_duplicates(const double* d_W, int M, int D, const int32_t* d_col_of_proto /*[M..] or NULL*/,
+                              float* d_wnorm, uint64_t* d_hash, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * K1  best-matching-unit search
  * replaces  BaseSom._get_winning_neurons(data, n_bmu)   dbgsom/BaseSom.py:446-464
@@ -142,6 +152,12 @@ typedef struct dbgsom_bmu_args {
   float scale;             /* the scale both shadows were built with */
   int32_t M;
   int32_t Mpad;
+  int32_t proto_stride;    /* optional hint, 0 = none: a value s > 0 promises d_proto_of_col[c] == (c * s) % Mpad
+                              for every c (s coprime to Mpad, Mpad < 65536); the candidate search then evaluates
+                              prototype indices in registers instead of loading them */
+  int32_t ties_any;        /* 1: prototypes with EQUAL approximate scores may be kept in any order (n_bmu = 1
+                              only, and only after dbgsom_exclude_duplicates); 0: ordered by prototype index, so
+                              the lowest index among exact copies always survives */
   /* request */
   int32_t n_bmu;           /* 1 or 2 */
   int32_t backend;         /* DBGSOM_BMU_SIMT / DBGSOM_BMU_TENSOR */

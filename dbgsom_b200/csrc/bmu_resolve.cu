@@ -67,56 +67,69 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) bmu_resolve_kernel(
   const int64_t nwarps = (int64_t)gridDim.x * WARPS_PER_BLOCK;
   unsigned long long n_amb = 0, n_ovf = 0, n_cand = 0, n_full = 0;
 
-  for (int64_t row = warp0; row < N; row += nwarps) {
-    const int cnt = cand_count[row];
-    const bool overflow = cnt == DBGSOM_CAND_OVERFLOW;
-    if (!overflow) n_cand += cnt;
-    // a single candidate for a single winner is already final (written by the front end)
-    if (NB == 1 && cnt == 1 && !want_dist) continue;
-    const float* x = X + row * ldx;
-    Top2 top;
-    top.init();
-    if (overflow) {
-      ++n_ovf;
-      bool full = true;
-      if (NB == 1 && xnorm16 != nullptr) {
-        // More than kMaxCand prototypes lie within 2 * bound of the best approximate score s1.  With s2 the
-        // second smallest approximate score and B the bound: every exact squared distance is >= s1 - B and
-        // the two prototypes behind s1, s2 are exactly <= s2 + B, so the exact best / second-best gap is at
-        // most (s2 - s1) + 2B and the exact minimum is at least db - 2B (db = exact distance of the approximate
-        // winner).  If that gap is under the tie tolerance the approximate winner is as good as any (see
-        // dbgsom_b200.h); the candidate search leaves s2 - s1 in the row's first candidate slot.
-        const int jb = idx_out[row];
-        const double db = sqdist_f64(x, W + (int64_t)jb * D, D, lane);
-        const double bound = (double)(tensor_score_bound(xnorm16[row], wmax, bound_coef) * inv_scale2);
-        const double gap = (double)(__int_as_float(cand_idx[row * kMaxCand]) * inv_scale2) + 2.0 * bound;
-        if (jb >= 0 && gap <= (double)tie_rel * (db - 2.0 * bound)) {
-          top.offer(db, jb);
-          full = false;
+  // 32 rows per warp step: every lane reads one row's candidate count (one coalesced load), then the warp
+  // works through the rows that need a re-score together.  In a training epoch > 99 % of the rows have a
+  // single candidate, which is already final (written by the front end); one warp per ROW spent most of this
+  // kernel's time discovering that.
+  for (int64_t base = warp0 * 32; base < N; base += nwarps * 32) {
+    const int64_t my_row = base + lane;
+    const int my_cnt = my_row < N ? cand_count[my_row] : 1;
+    if (my_row < N && my_cnt != DBGSOM_CAND_OVERFLOW) n_cand += my_cnt;
+    unsigned todo = __ballot_sync(kFullMask, my_row < N && !(NB == 1 && my_cnt == 1 && !want_dist));
+    while (todo) {
+      const int src_lane = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int64_t row = base + src_lane;
+      const int cnt = __shfl_sync(kFullMask, my_cnt, src_lane);
+      const bool overflow = cnt == DBGSOM_CAND_OVERFLOW;
+      const float* x = X + row * ldx;
+      Top2 top;
+      top.init();
+      if (overflow) {
+        ++n_ovf;
+        bool full = true;
+        if (NB == 1 && xnorm16 != nullptr) {
+          // More than kMaxCand prototypes lie within 2 * bound of the best approximate score s1.  With s2 the
+          // second smallest approximate score and B the bound: every exact squared distance is >= s1 - B and
+          // the two prototypes behind s1, s2 are exactly <= s2 + B, so the exact best / second-best gap is at
+          // most (s2 - s1) + 2B and the exact minimum is at least db - 2B (db = exact distance of the approximate
+          // winner).  If that gap is under the tie tolerance the approximate winner is as good as any (see
+          // dbgsom_b200.h); the candidate search leaves s2 - s1 in the row's first candidate slot.
+          const int jb = idx_out[row];
+          const double db = sqdist_f64(x, W + (int64_t)jb * D, D, lane);
+          const double bound = (double)(tensor_score_bound(xnorm16[row], wmax, bound_coef) * inv_scale2);
+          const double gap = (double)(__int_as_float(cand_idx[row * kMaxCand]) * inv_scale2) + 2.0 * bound;
+          if (jb >= 0 && gap <= (double)tie_rel * (db - 2.0 * bound)) {
+            top.offer(db, jb);
+            full = false;
+          }
+        }
+        if (full) {
+          ++n_full;
+          if (lane == 0) rescan_rows[atomicAdd(rescan_count, 1)] = (int32_t)row;
+          continue;  // written by bmu_rescan_kernel
+        }
+      } else {
+        if (cnt > NB) ++n_amb;
+        const int my = lane < kMaxCand ? cand_idx[row * kMaxCand + lane] : -1;
+        for (int q = 0; q < cnt; ++q) {
+          const int j = __shfl_sync(kFullMask, my, q);
+          top.offer(sqdist_f64(x, W + (int64_t)j * D, D, lane), j);
         }
       }
-      if (full) {
-        ++n_full;
-        if (lane == 0) rescan_rows[atomicAdd(rescan_count, 1)] = (int32_t)row;
-        continue;  // written by bmu_rescan_kernel
-      }
-    } else {
-      if (cnt > NB) ++n_amb;
-      const int my = lane < kMaxCand ? cand_idx[row * kMaxCand + lane] : -1;
-      for (int q = 0; q < cnt; ++q) {
-        const int j = __shfl_sync(kFullMask, my, q);
-        top.offer(sqdist_f64(x, W + (int64_t)j * D, D, lane), j);
-      }
-    }
-    if (lane == 0) {
-      idx_out[row * NB] = top.i1;
-      if (NB == 2) idx_out[row * NB + 1] = top.i2;
-      if (want_dist) {
-        dist_out[row * NB] = sqrt(top.d1);
-        if (NB == 2) dist_out[row * NB + 1] = sqrt(top.d2);
+      if (lane == 0) {
+        idx_out[row * NB] = top.i1;
+        if (NB == 2) idx_out[row * NB + 1] = top.i2;
+        if (want_dist) {
+          dist_out[row * NB] = sqrt(top.d1);
+          if (NB == 2) dist_out[row * NB + 1] = sqrt(top.d2);
+        }
       }
     }
   }
+  // n_cand was counted per lane (its own rows), the other three per warp (uniform)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n_cand += __shfl_xor_sync(kFullMask, n_cand, o);
   if (stats != nullptr && lane == 0 && (n_amb | n_ovf | n_cand | n_full)) {
     atomicAdd(stats + 0, n_amb);
     atomicAdd(stats + 1, n_ovf);
@@ -234,7 +247,7 @@ int launch_rescan(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t
 }  // namespace
 
 int launch_bmu_resolve(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t s) {
-  int64_t blocks = ceil_div<int64_t>(a.N, WARPS_PER_BLOCK);
+  int64_t blocks = ceil_div<int64_t>(a.N, WARPS_PER_BLOCK * 32);  // a warp takes 32 rows per step
   if (blocks > 148 * 16) blocks = 148 * 16;  // grid-stride beyond 16 resident CTAs per SM
   auto* stats = reinterpret_cast<unsigned long long*>(a.d_stats);
   const bool shortcut = a.backend == DBGSOM_BMU_TENSOR && !a.strict;

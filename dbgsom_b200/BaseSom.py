@@ -12,6 +12,8 @@ sigma schedule, thresholds, early stopping, and the fitted NetworkX graph `som_`
 
 from __future__ import annotations
 
+import os
+import time
 from math import exp, log, sqrt
 from typing import Any
 
@@ -154,10 +156,27 @@ class BaseSom(BaseEstimator):
             self.classes_ = np.array(classes)
         self.random_state_ = check_random_state(self.random_state)
         engine = self._make_engine()
+        profile = os.environ.get("DBGSOM_PROFILE") == "1"  # wall time per stage + device time per kernel phase
+        if profile and hasattr(engine, "enable_profiling"):
+            engine.enable_profiling(True)
+        self._host_growth_s = 0.0
+        self._host_hops_s = 0.0
         try:
+            t0 = time.perf_counter()
             self._initialize_som(engine, X, y)
+            t1 = time.perf_counter()
             self._grow_som(engine)
+            t2 = time.perf_counter()
             self._finalize(engine, y)
+            t3 = time.perf_counter()
+            if profile:
+                self.fit_profile_ = {
+                    "initialize_s": t1 - t0, "epochs_s": t2 - t1, "finalize_s": t3 - t2,
+                    "host_growth_s": self._host_growth_s, "hops_s": self._host_hops_s,
+                    "finalize": {k: float(v) for k, v in self._finalize_profile.items()},
+                }
+                if hasattr(engine, "phase_times_ms"):
+                    self.fit_profile_["device_ms"] = {k: round(float(np.sum(v)), 2) for k, v in engine.phase_times_ms().items()}
         finally:
             engine.close()
         self.n_features_in_ = X.shape[1]
@@ -226,7 +245,9 @@ class BaseSom(BaseEstimator):
             if self._hops_dirty:
                 # the reference recomputes all-pairs hops every epoch (quirk Q3); they only
                 # change when the map grew
+                th = time.perf_counter()
                 engine.set_hops_from_topology(topo)
+                self._host_hops_s += time.perf_counter() - th
                 self._hops_dirty = False
             result = engine.epoch(
                 sigma=self._current_sigma(),
@@ -247,11 +268,13 @@ class BaseSom(BaseEstimator):
                 and len(topo) < self.max_neurons
                 and epoch % self.convergence_iter == self.convergence_iter - 1
             ):
+                tg = time.perf_counter()
                 topo.distribute_errors(self.growing_threshold_)
                 ops = topo.grow(self.growing_threshold_, epoch)
                 if ops:
                     engine.apply_row_ops(ops, n_rows=len(topo))
                     self._hops_dirty = True
+                self._host_growth_s += time.perf_counter() - tg
 
     # ------------------------------------------------------------------ after the loop
     def _finalize(self, engine, y) -> None:
@@ -264,6 +287,7 @@ class BaseSom(BaseEstimator):
         (`engine.final_statistics`, `engine.label_histogram`); only per-neuron vectors come back.
         """
         topo = self._topology
+        tf = [time.perf_counter()]
         # Quirk kept for parity: after the loop the reference's `weights_` / `neurons_` still
         # hold the state from the START of the last epoch (they are refreshed at the top of
         # the loop body, dbgsom/BaseSom.py:397-401), so topographic error, quantisation
@@ -271,6 +295,7 @@ class BaseSom(BaseEstimator):
         # update, while the graph (and the final `weights_`) carry the updated ones.
         st = engine.final_statistics(topo.positions(), topo.degrees())
         n_total = engine.n_samples_global
+        tf.append(time.perf_counter())
         # topographic error: grid distance of the two BMUs > 1.5 (dbgsom/BaseSom.py:924-953)
         self.topographic_error_ = st["te_count"] / n_total
         self.quantization_error_ = st["qe_sum"] / n_total
@@ -301,14 +326,31 @@ class BaseSom(BaseEstimator):
         self._topology = topo.without(dead)
         self.neurons_ = list(graph.nodes)
         self.weights_ = weights[alive]
-        self._distance_matrix = self._topology.hop_matrix()
+        self._distance_matrix_cache = None  # all-pairs hops of the reduced map: built on first use (`_distance_matrix`)
 
         # prototype labels and `labels_` use the UPDATED, reduced map (dbgsom/BaseSom.py:121,
         # :127; SomVQ.py:150-152; SomClassifier.py:130-152): one more BMU pass, kept on the device
+        tf.append(time.perf_counter())
         engine.keep_rows(alive)
         engine.final_winners()
+        tf.append(time.perf_counter())
         self._label_prototypes(y, engine)
         self._fit(engine)
+        tf.append(time.perf_counter())
+        self._finalize_profile = dict(zip(("statistics_s", "graph_s", "final_winners_s", "labels_s"), np.diff(tf).round(4)))
+
+    @property
+    def _distance_matrix(self) -> np.ndarray:
+        """All-pairs hop counts of the fitted map, float64 with inf between components -- the reference's
+        `_distance_matrix` (dbgsom/BaseSom.py:235).  Nothing in `fit`/`predict`/`transform` reads it, and it
+        is M x M float64 (2 GB at 16k neurons), so it is built on first access instead of inside `fit`."""
+        if getattr(self, "_distance_matrix_cache", None) is None:
+            self._distance_matrix_cache = self._topology.hop_matrix()
+        return self._distance_matrix_cache
+
+    @_distance_matrix.setter
+    def _distance_matrix(self, value) -> None:
+        self._distance_matrix_cache = value
 
     # ------------------------------------------------------------------ inference helpers
     def _get_winning_neurons(self, data, n_bmu: int):

@@ -131,6 +131,72 @@ def test_bmu_duplicate_prototypes_lowest_index_wins():
         e.close()
 
 
+def test_bmu_collapsed_cluster_of_near_identical_prototypes():
+    """Late in a fit large dead regions of the map collapse onto one centre: thousands of prototypes that
+    agree to ~1e-7 (identical fp16 shadows, distinct float64 rows) plus exact copies.  For the samples of that
+    centre every one of them lies inside the error bound, which drives the epilogue's gate / eviction paths,
+    the flagged-row policy and the float64 re-scan; winners must still equal the oracle's outside the 1e-6
+    near-tie set, with and without strict ties, for one and two winners."""
+    n, d, m = 20000, 128, 2048
+    X = _datasets.gmm(n, d, 16, 4)
+    rng = np.random.default_rng(9)
+    W = X[rng.choice(n, m, replace=False)].astype(np.float64)
+    centre = X[X.shape[0] // 2].astype(np.float64) + 0.01
+    blob = np.arange(300, 1500)
+    W[blob] = centre * (1.0 + 1e-7 * rng.standard_normal((blob.size, 1))) + 1e-7 * rng.standard_normal((blob.size, d))
+    W[1500:1540] = W[310]  # exact copies of a blob member
+    W[40:50] = W[7]        # and of an ordinary prototype
+    ref_gap = O.relative_gap(X, W)
+    _, ref = O.bmu_expansion(X, W, 1)
+    ok = ref_gap >= GAP
+    flagged_seen = 0
+    for kw in (dict(), dict(strict_ties=True)):
+        e = engine(bmu_backend="tensor", **kw)
+        _, idx = e.bmu(X, W, 1)
+        st = e.bmu_stats_host()
+        flagged_seen += st["flagged"]
+        np.testing.assert_array_equal(idx[ok, 0], ref[ok])
+        assert_bmu_parity(idx[:, 0], X, W, ref)
+        # the lowest index among exact copies wins
+        assert not np.isin(idx[:, 0], np.arange(1500, 1540)).any() and not np.isin(idx[:, 0], np.arange(40, 50)).any()
+        dist2, idx2 = e.bmu(X, W, 2)
+        np.testing.assert_array_equal(idx2[ok, 0], ref[ok])
+        assert (dist2[:, 0] <= dist2[:, 1]).all() and (idx2[:, 0] != idx2[:, 1]).all()
+        e.close()
+    assert flagged_seen > 0, "the collapsed cluster should overflow the candidate tables of its samples"
+
+
+def test_exclude_duplicates_marks_only_later_copies():
+    """dbgsom_exclude_duplicates: wnorm = +inf exactly for prototypes equal to a lower-indexed one."""
+    import torch
+
+    from dbgsom_b200 import _native as nat
+
+    lib = nat.load()
+    rng = np.random.default_rng(0)
+    m, d = 700, 64
+    W = rng.normal(size=(m, d))
+    W[300] = W[5]
+    W[650] = W[5]
+    W[12] = W[11]
+    W[400, 3] = -0.0
+    W[401] = W[400]
+    W[401, 3] = 0.0  # -0.0 == +0.0: still a copy
+    W[500] = W[499]
+    W[500, 17] += 1e-12  # not a copy
+    dev = torch.device("cuda", 0)
+    dW = torch.from_numpy(W).to(dev)
+    col = torch.from_numpy(rng.permutation(768).astype(np.int32)).to(dev)
+    wnorm = torch.zeros(768, dtype=torch.float32, device=dev)
+    scratch = torch.empty(m, dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    nat.check(lib.dbgsom_exclude_duplicates(dW.data_ptr(), m, d, col.data_ptr(), wnorm.data_ptr(), scratch.data_ptr(), stream), "x")
+    torch.cuda.synchronize(dev)
+    marked = np.flatnonzero(np.isinf(wnorm.cpu().numpy()))
+    expect = np.sort(col.cpu().numpy()[[300, 650, 12, 401]])
+    np.testing.assert_array_equal(marked, expect)
+
+
 def test_bmu_ragged_and_tiny_shapes():
     rng = np.random.default_rng(0)
     for n, d, m in [(4, 3, 4), (1, 5, 2), (129, 17, 5), (1000, 65, 257), (257, 2, 300)]:

@@ -32,6 +32,7 @@
 // row tile so that only prototypes stream from L2.
 #include <cuda.h>
 
+#include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -173,6 +174,52 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- CTA pair (cta_group::2): one MMA stream for two SMs.  The leader CTA (cluster rank 0) issues every
+// tcgen05.mma / tcgen05.cp / tcgen05.commit for both; each CTA keeps its own sample rows in its own tensor
+// memory and holds HALF of every prototype tile in its own shared memory (the pair exchanges the halves inside
+// the TPC), so shared-memory reads and TMA writes per SM are half of the single-CTA form.
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t cta_addr, uint32_t rank) {  // shared::cluster address in `rank`
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  // default semantics (release at CTA scope), like CUTLASS' ClusterBarrier::arrive(cta_id): the data this barrier
+  // guards moves through the async / tensor proxies, whose ordering comes from complete_tx and the tcgen05 fences;
+  // `.release.cluster` put a full error-barrier fence (~300 cycles) in front of every arrive
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load into MY shared memory, completion bytes counted on the barrier at `bar_cluster_addr` (the leader's)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int x,
+                                                 int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(map), "r"(bar_cluster_addr), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_ts_pair(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                                   uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_cp_128x256b_pair(uint32_t tmem_dst, uint64_t desc_src) {
+  asm volatile("tcgen05.cp.cta_group::2.128x256b [%0], %1;" ::"r"(tmem_dst), "l"(desc_src) : "memory");
+}
+
 // K-major operand tile in shared memory, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart.
 // (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
 // layout SWIZZLE_128B=2 [61,64).)
@@ -295,7 +342,7 @@ struct Cfg {
 };
 
 struct Barriers {
-  uint64_t full[8], empty[8];
+  uint64_t full[16], empty[16];
   uint64_t a_full, a_empty;
   uint64_t tmem_full[4], tmem_empty[4];
   uint32_t tmem_base;
@@ -308,7 +355,7 @@ struct Barriers {
 // shadow matrix per 128 sample rows: 7 TB/s at config 3, which is what kept the tensor pipe at 78 %)
 // drops by CL.  A ring stage is free again when the MMA warps of ALL CL CTAs have consumed it (their
 // commits arrive on every CTA's `empty` barrier).
-template <int NPASS, int NB, int BN, int RES_KB, int AKB, int CL>
+template <int NPASS, int NB, int BN, int RES_KB, int AKB, int CL, bool PAIR = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     bmu_cand_tensor_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                            const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
@@ -320,6 +367,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                            uint8_t* __restrict__ cand_count) {
   using C = Cfg<NPASS, BN, RES_KB, AKB>;
   constexpr bool ATM = C::ATM;
+  static_assert(!PAIR || (ATM && CL == 2), "the CTA-pair form needs the sample tile in tensor memory and a cluster of two");
+  constexpr int B_PART_BYTES = PAIR ? C::B_TILE_BYTES / 2 : C::B_TILE_BYTES;  // prototype tile bytes per CTA and shadow
+  // pair: the ring is cut into 16 KB slots -- one k-block of one sample shadow, or one k-block of my half of both
+  // prototype shadows -- so the same shared memory holds twice as many k-blocks in flight
+  constexpr int SLOT_BYTES = PAIR ? A_TILE_BYTES : C::STAGE_BYTES;
+  constexpr int NSLOT = PAIR ? (C::STAGES * C::STAGE_BYTES / A_TILE_BYTES > 16 ? 16 : C::STAGES * C::STAGE_BYTES / A_TILE_BYTES)
+                             : C::STAGES;
+  static_assert(!PAIR || C::NA * B_PART_BYTES <= SLOT_BYTES, "a prototype k-block of the pair form must fit a slot");
   constexpr int NACC = C::NACC;
   constexpr bool XRES = C::XRES;
   constexpr bool ASTREAM = C::ASTREAM;
@@ -356,23 +411,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(&bars->full[s], 1);
-      mbar_init(&bars->empty[s], CL);
+    for (int s = 0; s < NSLOT; ++s) {
+      mbar_init(&bars->full[s], PAIR ? 2 : 1);   // pair: the leader's expect_tx arrive + the peer producer's arrive
+      mbar_init(&bars->empty[s], PAIR ? 1 : CL);  // pair: one MMA stream frees the stage in both CTAs
     }
     mbar_init(&bars->a_full, 1);
     mbar_init(&bars->a_empty, 1);
     for (int b = 0; b < NACC; ++b) {
       mbar_init(&bars->tmem_full[b], 1);
-      mbar_init(&bars->tmem_empty[b], EPI_THREADS);
+      mbar_init(&bars->tmem_empty[b], PAIR ? 2 * EPI_WARPS : EPI_THREADS);  // pair: one arrive per epilogue warp of both CTAs
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
-                 "r"((uint32_t)C::TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
+                   "r"((uint32_t)C::TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
+                   "r"((uint32_t)C::TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -398,6 +460,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
         if (ATM) {  // the sample tile's k-blocks travel through the ring once per row tile
           for (int kb = 0; kb < KB; ++kb) {
+            if (PAIR) {  // one slot per shadow; both CTAs' bytes are counted on the leader's barrier
+              for (int h = 0; h < C::NA; ++h) {
+                mbar_wait(&bars->empty[stage], phase ^ 1);
+                const uint32_t lead_full = mapa_u32(smem_u32(&bars->full[stage]), 0);
+                if (cl_rank == 0) mbar_expect_tx(&bars->full[stage], (uint32_t)(2 * A_TILE_BYTES));
+                else mbar_arrive_cluster(lead_full);
+                tma_load_2d_pair(stages + stage * SLOT_BYTES, h == 0 ? &map_xh : &map_xl, lead_full, kb * BK, row0);
+                if (++stage == NSLOT) {
+                  stage = 0;
+                  phase ^= 1;
+                }
+              }
+              continue;
+            }
             mbar_wait(&bars->empty[stage], phase ^ 1);
             uint8_t* st = stages + stage * C::STAGE_BYTES;
             mbar_expect_tx(&bars->full[stage], (uint32_t)(C::NA * A_TILE_BYTES));
@@ -412,7 +488,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         for (int nt = 0; nt < NT; ++nt) {
           for (int kb = 0; kb < KB; ++kb) {
             mbar_wait(&bars->empty[stage], phase ^ 1);
-            uint8_t* st = stages + stage * C::STAGE_BYTES;
+            uint8_t* st = stages + stage * SLOT_BYTES;
+            if (PAIR) {  // my half of the prototype tile (rows [rank * BN/2, +BN/2)) into MY shared memory only
+              const uint32_t lead_full = mapa_u32(smem_u32(&bars->full[stage]), 0);
+              if (cl_rank == 0) mbar_expect_tx(&bars->full[stage], (uint32_t)(2 * C::NA * B_PART_BYTES));
+              else mbar_arrive_cluster(lead_full);
+              const int prow = nt * BN + (int)cl_rank * (BN / 2);
+              tma_load_2d_pair(st, &map_wh, lead_full, kb * BK, prow);
+              if (NPASS == 3) tma_load_2d_pair(st + B_PART_BYTES, &map_wl, lead_full, kb * BK, prow);
+              if (++stage == NSLOT) {
+                stage = 0;
+                phase ^= 1;
+              }
+              continue;
+            }
             mbar_expect_tx(&bars->full[stage], (uint32_t)C::STAGE_BYTES);
             if (CL == 1) {
               tma_load_2d(st, &map_wh, &bars->full[stage], kb * BK, nt * BN);
@@ -436,10 +525,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
       }
     }
-  } else if (warp == 1) {
-    // ================================================================ MMA issuer
+  } else if (warp == 1 && (!PAIR || cl_rank == 0)) {
+    // ================================================================ MMA issuer (pair: the leader CTA only)
     if (elect_one()) {
-      constexpr uint32_t idesc = instr_desc_f16(BM, BN);
+      constexpr uint32_t idesc = instr_desc_f16(PAIR ? 2 * BM : BM, BN);
       int stage = 0;
       uint32_t phase = 0, a_phase = 0, acc = 0, acc_phase = 0;
       for (int64_t it = 0; it < n_iters; ++it) {
@@ -452,6 +541,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           // tcgen05.cp and tcgen05.mma execute in issue order, so these copies run after the previous row
           // tile's MMAs have read the old sample tile and before this row tile's MMAs read the new one
           for (int kb = 0; kb < KB; ++kb) {
+            if (PAIR) {  // one slot per shadow; each CTA's staged rows go to its own tensor memory
+              for (int h = 0; h < C::NA; ++h) {
+                mbar_wait(&bars->full[stage], phase);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(stages + stage * SLOT_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k)
+                  tc_cp_128x256b_pair(tmem_a + h * AKB * (BK / 2) + kb * (BK / 2) + k * 8,
+                                      smem_desc_sw128(sa + k * UMMA_K * 2));
+                tc_commit_pair(&bars->empty[stage], cl_mask);
+                if (++stage == NSLOT) {
+                  stage = 0;
+                  phase ^= 1;
+                }
+              }
+              continue;
+            }
             mbar_wait(&bars->full[stage], phase);
             tc_fence_after();
             const uint32_t sa = smem_u32(stages + stage * C::STAGE_BYTES);
@@ -476,16 +582,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           for (int kb = 0; kb < KB; ++kb) {
             mbar_wait(&bars->full[stage], phase);
             tc_fence_after();
-            uint8_t* st = stages + stage * C::STAGE_BYTES;
+            uint8_t* st = stages + stage * SLOT_BYTES;
             const uint32_t b_hi = smem_u32(st);
-            const uint32_t b_lo = b_hi + C::B_TILE_BYTES;
+            const uint32_t b_lo = b_hi + B_PART_BYTES;
             const uint32_t a_hi = XRES ? smem_u32(res_a + kb * C::NA * A_TILE_BYTES)
                                        : smem_u32(st + C::NA * C::B_TILE_BYTES);
             const uint32_t a_lo = a_hi + A_TILE_BYTES;
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint32_t koff = k * UMMA_K * 2;  // bytes along K inside the swizzle atom
-              if (ATM) {
+              if (PAIR) {
+                const uint32_t ta_hi = tmem_a + kb * (BK / 2) + k * 8;
+                const uint32_t ta_lo = ta_hi + AKB * (BK / 2);
+                tc_mma_f16_ts_pair(tmem_d, ta_hi, smem_desc_sw128(b_hi + koff), idesc, (kb | k) != 0);
+                if (NPASS == 3) {
+                  tc_mma_f16_ts_pair(tmem_d, ta_hi, smem_desc_sw128(b_lo + koff), idesc, 1);
+                  tc_mma_f16_ts_pair(tmem_d, ta_lo, smem_desc_sw128(b_hi + koff), idesc, 1);
+                }
+              } else if (ATM) {
                 const uint32_t ta_hi = tmem_a + kb * (BK / 2) + k * 8;
                 const uint32_t ta_lo = ta_hi + AKB * (BK / 2);
                 tc_mma_f16_ts(tmem_d, ta_hi, smem_desc_sw128(b_hi + koff), idesc, (kb | k) != 0);
@@ -502,13 +616,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
               }
             }
             // frees the smem stage (in every CTA of the cluster) once these MMAs have read it
-            if (CL == 1) tc_commit(&bars->empty[stage]); else tc_commit_mc(&bars->empty[stage], cl_mask);
-            if (++stage == C::STAGES) {
+            if (PAIR) tc_commit_pair(&bars->empty[stage], cl_mask);
+            else if (CL == 1) tc_commit(&bars->empty[stage]); else tc_commit_mc(&bars->empty[stage], cl_mask);
+            if (++stage == NSLOT) {
               stage = 0;
               phase ^= 1;
             }
           }
-          tc_commit(&bars->tmem_full[acc]);  // accumulator complete -> epilogue
+          // accumulator complete -> epilogue (pair: of both CTAs)
+          if (PAIR) tc_commit_pair(&bars->tmem_full[acc], cl_mask); else tc_commit(&bars->tmem_full[acc]);
           if (++acc == NACC) {
             acc = 0;
             acc_phase ^= 1;
@@ -662,7 +778,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           }
         }
         tc_fence_before();
-        mbar_arrive(&bars->tmem_empty[acc]);
+        if (PAIR) {  // one arrive per warp, on the leader's barrier
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->tmem_empty[acc]), 0));
+        } else {
+          mbar_arrive(&bars->tmem_empty[acc]);
+        }
         if (++acc == NACC) {
           acc = 0;
           acc_phase ^= 1;
@@ -726,8 +847,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   if (CL > 1) cluster_sync_all();  // no CTA leaves while a peer may still write its shared memory or barriers
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
-                 : "memory");
+    if (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
+                   : "memory");
   }
 }
 
@@ -775,7 +900,7 @@ int sm_count() {
   return n;
 }
 
-template <int NPASS, int NB, int BN, int RES_KB, int AKB, int CL>
+template <int NPASS, int NB, int BN, int RES_KB, int AKB, int CL, bool PAIR = false>
 int launch_cfg_cl(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t s) {
   using C = Cfg<NPASS, BN, RES_KB, AKB>;
   CUtensorMap mxh, mxl, mwh, mwl;
@@ -792,7 +917,7 @@ int launch_cfg_cl(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t
     mxl = mxh;
     mwl = mwh;
   }
-  auto kern = bmu_cand_tensor_kernel<NPASS, NB, BN, RES_KB, AKB, CL>;
+  auto kern = bmu_cand_tensor_kernel<NPASS, NB, BN, RES_KB, AKB, CL, PAIR>;
   DBGSOM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   const int KB = (int)(a.ld16 / BK);
   const int NT = a.Mpad / BN;  // prototypes are permuted over all Mpad shadow rows
@@ -847,6 +972,17 @@ template <int NPASS, int NB, int BN, int RES_KB, int AKB = 0>
 int launch_cfg(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t s) {
   // small problems (fewer row tiles than SMs) gain nothing from sharing
   const int cl = ceil_div<int64_t>(a.N, BM) < sm_count() ? 1 : cluster_size();
+  if constexpr (AKB > 0) {  // CTA pairs (cta_group::2) whenever the sample tile is tensor-memory resident; DBGSOM_TC_PAIR=0 disables
+    static const bool pair = getenv("DBGSOM_TC_PAIR") == nullptr || atoi(getenv("DBGSOM_TC_PAIR")) != 0;
+    if (pair && cl >= 2) {
+      static bool said = false;
+      if (!said && getenv("DBGSOM_TC_VERBOSE")) {
+        said = true;
+        fprintf(stderr, "dbgsom: K1 runs as CTA pairs (cta_group::2)\n");
+      }
+      return launch_cfg_cl<NPASS, NB, BN, RES_KB, AKB, 2, true>(a, ws, s);
+    }
+  }
   if (cl == 4) return launch_cfg_cl<NPASS, NB, BN, RES_KB, AKB, 4>(a, ws, s);
   if (cl == 2) return launch_cfg_cl<NPASS, NB, BN, RES_KB, AKB, 2>(a, ws, s);
   return launch_cfg_cl<NPASS, NB, BN, RES_KB, AKB, 1>(a, ws, s);

@@ -1,0 +1,61 @@
+"""Winners of the tensor back end against the fp32 SIMT back end (both followed by the exact float64 re-score) on
+a bench-like problem; prints the number of differing rows and how many of those differ by more than a 1e-7 relative
+float64 gap.  Used to validate kernel variants selected by environment switches (DBGSOM_TC_PAIR, DBGSOM_TC_CLUSTER).
+
+    python tools/check_backends.py [rows] [d] [m] [epochs]
+"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import torch  # noqa: E402
+
+from bench import grid_hops, make_shard, sigma_at  # noqa: E402
+from dbgsom_b200 import _native as nat  # noqa: E402
+from dbgsom_b200.engine import DeviceEngine  # noqa: E402
+
+
+def main():
+    rows = int(sys.argv[1]) if len(sys.argv) > 1 else 400_000
+    d = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+    m = int(sys.argv[3]) if len(sys.argv) > 3 else 4096
+    epochs = int(sys.argv[4]) if len(sys.argv) > 4 else 4
+    side = int(round(m ** 0.5))
+    dev = torch.device("cuda", 0)
+    X = make_shard(torch, dev, rows, d, 64, 0)
+    eng = DeviceEngine(device="cuda:0", bmu_backend="tensor")
+    eng.load_device_data(X)
+    eng.init_map_from_rows(np.random.default_rng(0).choice(rows, m, replace=False), capacity=m)
+    eng.set_hops(grid_hops(side))
+    total_bad = 0
+    for e in range(epochs):
+        W = eng.W[eng.cur]
+        eng._ensure_x16(True)
+        x16 = (eng.X16_hi, eng.X16_lo, eng.xnorm16)
+        ref = torch.empty((rows, 1), dtype=torch.int32, device=dev)
+        got = torch.empty((rows, 1), dtype=torch.int32, device=dev)
+        eng.strict_ties = True
+        eng._run_bmu(eng.X, rows, eng.ldx, None, W, m, 1, False, ref, None, backend=(nat.BMU_SIMT, 0))
+        eng.strict_ties = False
+        eng._run_bmu(eng.X, rows, eng.ldx, x16, W, m, 1, False, got, None, backend=(nat.BMU_TENSOR, 3))
+        diff = torch.nonzero(got[:, 0] != ref[:, 0])[:, 0]
+        bad = 0
+        if diff.numel():
+            xs = eng.X[diff][:, :d].double()
+            Wd = W[:m, :d]
+            da = ((xs - Wd[got[diff, 0].long()]) ** 2).sum(1)
+            db = ((xs - Wd[ref[diff, 0].long()]) ** 2).sum(1)
+            rel = (da - db).abs() / torch.minimum(da, db).clamp_min(1e-300)
+            bad = int((rel > 1e-7).sum())
+        total_bad += bad
+        print(f"epoch {e}: {int(diff.numel())} rows differ, {bad} of them beyond a 1e-7 relative gap; min idx {int(got.min())}", flush=True)
+        eng.epoch(sigma_at(e, m), True, False)
+    print("OK" if total_bad == 0 else "MISMATCH")
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()

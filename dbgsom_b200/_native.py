@@ -13,7 +13,7 @@ _LIB = None
 LIB_NAME = "libdbgsom_b200.so"
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_CAND = 8
 BMU_SIMT = 0
 BMU_TENSOR = 1
@@ -39,6 +39,8 @@ class BmuArgs(C.Structure):
         ("d_W16_hi", c_void_p),
         ("d_W16_lo", c_void_p),
         ("d_wnorm", c_void_p),
+        ("d_Wb16", c_void_p),
+        ("d_bias_scale", c_void_p),
         ("d_wmax", c_void_p),
         ("d_proto_of_col", c_void_p),
         ("scale", c_float),
@@ -116,6 +118,7 @@ SIGNATURES = {
          c_void_p, c_void_p, c_void_p, c_void_p],
     ),
     "dbgsom_exclude_duplicates": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dbgsom_prepare_bias": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dbgsom_bmu_workspace_bytes": (c_size_t, [c_int64, c_int32]),
     "dbgsom_bmu": (c_int, [C.POINTER(BmuArgs), c_void_p]),
     "dbgsom_bmu_candidates": (c_int, [C.POINTER(BmuArgs), c_void_p]),

@@ -216,6 +216,18 @@ __device__ __forceinline__ void tc_mma_f16_ts_pair(uint32_t tmem_d, uint32_t tme
       "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with the A operand from shared memory (each CTA's own tile at the same offset)
+__device__ __forceinline__ void tc_mma_f16_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                   uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tc_cp_128x256b_pair(uint32_t tmem_dst, uint64_t desc_src) {
   asm volatile("tcgen05.cp.cta_group::2.128x256b [%0], %1;" ::"r"(tmem_dst), "l"(desc_src) : "memory");
 }
@@ -359,6 +371,7 @@ template <int NPASS, int NB, int BN, int RES_KB, int AKB, int CL, bool PAIR = fa
 __global__ void __launch_bounds__(TC_THREADS, 1)
     bmu_cand_tensor_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                            const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
+                           const __grid_constant__ CUtensorMap map_wb, const float* __restrict__ bias_scale,
                            int64_t N, int KB, int NT, const float* __restrict__ wnorm,
                            const int32_t* __restrict__ proto_of_col, int pstride, int ties_any,
                            const float* __restrict__ xnorm16,
@@ -382,13 +395,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* res_a = smem;                               // [kb][hi|lo] A tiles (XRES)
   uint8_t* stages = smem + C::RES_BYTES;               // ring
-  uint8_t* ring = stages + C::STAGES * C::STAGE_BYTES;  // candidate tables
+  // wnorm staging, or -- in bias mode -- the constant A tile of the bias k-step (1024-byte aligned for its descriptor)
+  float* wn_smem = reinterpret_cast<float*>(stages + C::STAGES * C::STAGE_BYTES);
+  uint8_t* ring = stages + C::STAGES * C::STAGE_BYTES + C::WN_BYTES;  // candidate tables
   Barriers* bars = reinterpret_cast<Barriers*>(ring + C::RING_BYTES);
   float* tab_val = reinterpret_cast<float*>(ring);
   int* tab_idx = reinterpret_cast<int*>(ring + BM * EPI_SUBS * KSUB * 4);  // = tab_val + kTabIdxOffset bytes
   float* row_min = reinterpret_cast<float*>(ring + BM * EPI_SUBS * KSUB * 8);
   float4* sub_state = reinterpret_cast<float4*>(ring + BM * EPI_SUBS * KSUB * 8 + BM * 4);
-  float* wn_smem = reinterpret_cast<float*>(ring + C::RING_BYTES + C::MISC_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -435,6 +449,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                    : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+  }
+  // bias mode (CTA pairs only): wnorm enters the accumulator through one extra k-step per output tile
+  // (dbgsom_prepare_bias).  Its A operand is constant: E = bias_scale[0] in the first three columns of every row, a
+  // 128 x 64 fp16 K-major tile with the 128-byte swizzle (16-byte chunk c of row r sits at chunk c ^ (r & 7)).
+  const float bias_E = (PAIR && bias_scale != nullptr) ? bias_scale[0] : 0.f;
+  const bool bias_mode = PAIR && bias_E > 0.f;
+  if (bias_mode) {
+    const uint32_t e16 = (uint32_t)__half_as_ushort(__float2half_rn(bias_E));
+    uint4* tile = reinterpret_cast<uint4*>(wn_smem);
+    for (int q = threadIdx.x; q < BM * 8; q += TC_THREADS) {
+      const int r = q >> 3, ch = q & 7;
+      tile[q] = ch == (r & 7) ? make_uint4(e16 | (e16 << 16), e16, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core reads
   }
   tc_fence_before();
   __syncthreads();
@@ -518,6 +546,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
               if (NPASS == 3) tma_load_2d(sa + A_TILE_BYTES, &map_xl, &bars->full[stage], kb * BK, row0);
             }
             if (++stage == C::STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          if (PAIR && bias_mode) {  // my half of the tile's bias rows: one more slot
+            mbar_wait(&bars->empty[stage], phase ^ 1);
+            const uint32_t lead_full = mapa_u32(smem_u32(&bars->full[stage]), 0);
+            if (cl_rank == 0) mbar_expect_tx(&bars->full[stage], (uint32_t)(2 * B_PART_BYTES));
+            else mbar_arrive_cluster(lead_full);
+            tma_load_2d_pair(stages + stage * SLOT_BYTES, &map_wb, lead_full, 0, nt * BN + (int)cl_rank * (BN / 2));
+            if (++stage == NSLOT) {
               stage = 0;
               phase ^= 1;
             }
@@ -623,6 +662,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
               phase ^= 1;
             }
           }
+          if (PAIR && bias_mode) {  // + E * (h + m + l) = -wnorm / 2: the accumulator is now -score / 2
+            mbar_wait(&bars->full[stage], phase);
+            tc_fence_after();
+            tc_mma_f16_ss_pair(tmem_d, smem_desc_sw128(smem_u32(wn_smem)), smem_desc_sw128(smem_u32(stages + stage * SLOT_BYTES)),
+                               idesc, 1);
+            tc_commit_pair(&bars->empty[stage], cl_mask);
+            if (++stage == NSLOT) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
           // accumulator complete -> epilogue (pair: of both CTAs)
           if (PAIR) tc_commit_pair(&bars->tmem_full[acc], cl_mask); else tc_commit(&bars->tmem_full[acc]);
           if (++acc == NACC) {
@@ -657,7 +707,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     // wnorm is read by every row for every chunk: keep it in shared memory when it fits (global / L1
     // loads showed up as the longest stall of the epilogue at D = 128)
     const int mpad = NT * BN;
-    const bool wn_in_smem = C::WN_SMEM_FLOATS > 0 && mpad <= C::WN_SMEM_FLOATS;
+    const bool wn_in_smem = !bias_mode && C::WN_SMEM_FLOATS > 0 && mpad <= C::WN_SMEM_FLOATS;
     if (wn_in_smem)
       for (int i = threadIdx.x - EPI_WARP0 * 32; i < mpad; i += EPI_THREADS) wn_smem[i] = wnorm[i];
     const float* wn_src = wn_in_smem ? wn_smem : wnorm;
@@ -682,8 +732,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           const int col = nt * BN + c * 32;
           const float4* wn4 = reinterpret_cast<const float4*>(wn_src + col);
           float4 w4[8];
+          if (bias_mode) {  // wnorm is already in the accumulator
 #pragma unroll
-          for (int g = 0; g < 8; ++g) w4[g] = wn4[g];
+            for (int g = 0; g < 8; ++g) w4[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+          } else {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) w4[g] = wn4[g];
+          }
           tmem_ld_wait();
           // pass A: smallest score(s) of the chunk
           float a1 = kInf, a2 = kInf;
@@ -917,6 +972,21 @@ int launch_cfg_cl(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t
     mxl = mxh;
     mwl = mwh;
   }
+  CUtensorMap mwb = mwh;
+  const bool with_bias = PAIR && a.d_Wb16 != nullptr && a.d_bias_scale != nullptr;
+  if (with_bias) {
+    rc = make_map(&mwb, a.d_Wb16, a.Mpad, BK, BN / CL);
+    if (rc) return rc;
+  }
+  if (with_bias && getenv("DBGSOM_TC_VERBOSE")) {
+    static bool said = false;
+    if (!said) {
+      said = true;
+      float e = -1.f;
+      cudaMemcpy(&e, a.d_bias_scale, sizeof(float), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "dbgsom: K1 takes wnorm through the bias k-step, E = %g\n", e);
+    }
+  }
   auto kern = bmu_cand_tensor_kernel<NPASS, NB, BN, RES_KB, AKB, CL, PAIR>;
   DBGSOM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   const int KB = (int)(a.ld16 / BK);
@@ -951,7 +1021,8 @@ int launch_cfg_cl(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t
   const float coef = tensor_bound_coef(NPASS, a.bound_scale);
   // the arithmetic form needs c * stride < 2^32 for every shadow row c
   const int pstride = a.proto_stride > 0 && a.Mpad <= 65535 && a.proto_stride < a.Mpad ? a.proto_stride : 0;
-  DBGSOM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, mxh, mxl, mwh, mwl, a.N, KB, NT, a.d_wnorm, a.d_proto_of_col, pstride,
+  DBGSOM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, mxh, mxl, mwh, mwl, mwb, with_bias ? a.d_bias_scale : (const float*)nullptr,
+                                     a.N, KB, NT, a.d_wnorm, a.d_proto_of_col, pstride,
                                      a.n_bmu == 1 ? a.ties_any : 0, a.d_xnorm16, a.d_wmax, coef, a.d_idx, ws.cand_idx, ws.cand_count));
   DBGSOM_LAUNCH_CHECK();
   return DBGSOM_OK;

@@ -8,6 +8,7 @@ int run_prepare_x16(const float*, int64_t, int, int64_t, const float*, float, ui
 int run_prepare_w(const double*, int, int, const float*, float, float*, uint16_t*, uint16_t*, int64_t, int,
                   const int32_t*, float*, double*, float*, cudaStream_t);
 int run_exclude_duplicates(const double*, int, int, const int32_t*, float*, unsigned long long*, cudaStream_t);
+int run_prepare_bias(const float*, int, const float*, uint16_t*, float*, cudaStream_t);
 int run_row_ops(double*, int, const int32_t*, int, cudaStream_t);
 int run_gather_rows(const float*, int64_t, int, const int64_t*, int, double*, cudaStream_t);
 size_t accumulate_workspace_bytes(int64_t, int);
@@ -102,6 +103,12 @@ int dbgsom_exclude_duplicates(const double* d_W, int M, int D, const int32_t* d_
   if (!d_W || !d_wnorm || !d_hash || M <= 0 || D <= 0) return DBGSOM_E_BADARG;
   return run_exclude_duplicates(d_W, M, D, d_col_of_proto, d_wnorm, reinterpret_cast<unsigned long long*>(d_hash),
                                 as_stream(stream));
+}
+
+int dbgsom_prepare_bias(const float* d_wnorm, int Mpad, const float* d_wmax, uint16_t* d_Wb16, float* d_bias_scale,
+                        void* stream) {
+  if (!d_wnorm || !d_wmax || !d_Wb16 || !d_bias_scale || Mpad <= 0) return DBGSOM_E_BADARG;
+  return run_prepare_bias(d_wnorm, Mpad, d_wmax, d_Wb16, d_bias_scale, as_stream(stream));
 }
 
 int dbgsom_bmu_candidates(const dbgsom_bmu_args* a, void* stream) {

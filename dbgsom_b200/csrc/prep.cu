@@ -229,6 +229,45 @@ __global__ void __launch_bounds__(256) mark_duplicates_kernel(const double* __re
   }
 }
 
+// ------------------------------------------------------------------------------------------ bias rows
+// wnorm folded into the MMA: the candidate kernel ends every output tile with one extra k-step whose A operand is
+// the constant E = 2^e in its first three columns and whose B operand holds three fp16 pieces (h, m, l) of
+// -wnorm_j / (2 E) in the first three columns of Wb16[c, :] (c = shadow row), so the accumulator becomes
+// x'.u - wnorm/2 = -score/2 and the epilogue needs no per-column load.  h + m + l carries 33 bits, the fp32 wnorm
+// 24; e is chosen from max |wnorm| so that |h| < 2^15.  +inf (padding, excluded copies) becomes h = -inf: the
+// accumulator is -inf, the score +inf.  bias_scale[0] = E, or 0 when max |wnorm| is outside what fp16 pieces can
+// carry (the kernel then keeps loading wnorm).
+__global__ void __launch_bounds__(256) bias_rows_kernel(const float* __restrict__ wnorm, int Mpad,
+                                                       const float* __restrict__ wmax, __half* __restrict__ Wb16,
+                                                       float* __restrict__ bias_scale) {
+  const float top = 0.5f * wmax[2];  // max |wnorm| / 2 over the real prototypes
+  int e = 0;
+  (void)frexpf(top, &e);             // top < 2^e
+  e -= 15;                            // |v| / 2^e < 2^15
+  if (e < -14) e = -14;
+  const bool ok = e <= 15 && top == top && top < 3.0e38f;
+  const float E = ok ? ldexpf(1.f, e) : 0.f;
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c == 0) bias_scale[0] = E;
+  if (c >= Mpad || !ok) return;
+  const float wn = wnorm[c];
+  __half h, m, l;
+  if (wn > 3.0e38f) {  // +inf: never a candidate
+    h = __ushort_as_half((unsigned short)0xFC00);  // -inf
+    m = l = __float2half_rn(0.f);
+  } else {
+    const float v = ldexpf(-0.5f * wn, -e);  // exact: power-of-two scaling
+    h = __float2half_rn(v);
+    const float r1 = v - __half2float(h);    // exact in fp32 (the pieces do not overlap)
+    m = __float2half_rn(r1);
+    l = __float2half_rn(r1 - __half2float(m));
+  }
+  __half* row = Wb16 + (int64_t)c * 64;
+  row[0] = h;
+  row[1] = m;
+  row[2] = l;
+}
+
 // ------------------------------------------------------------------------------------------ rows
 // Sequential prototype-row arithmetic of the growth step (dbgsom/BaseSom.py:641-644, :705-726,
 // :824-827, :835-837): one CTA, ops in list order, a block barrier between ops.
@@ -297,6 +336,12 @@ int run_exclude_duplicates(const double* W, int M, int D, const int32_t* col_of_
   row_hash_kernel<<<M, 128, 0, s>>>(W, M, D, hash);
   DBGSOM_LAUNCH_CHECK();
   mark_duplicates_kernel<<<ceil_div(M, 256), 256, 0, s>>>(W, M, D, hash, col_of_proto, wnorm);
+  DBGSOM_LAUNCH_CHECK();
+  return DBGSOM_OK;
+}
+
+int run_prepare_bias(const float* wnorm, int Mpad, const float* wmax, uint16_t* Wb16, float* bias_scale, cudaStream_t s) {
+  bias_rows_kernel<<<ceil_div(Mpad, 256), 256, 0, s>>>(wnorm, Mpad, wmax, reinterpret_cast<__half*>(Wb16), bias_scale);
   DBGSOM_LAUNCH_CHECK();
   return DBGSOM_OK;
 }

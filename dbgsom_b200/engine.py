@@ -413,6 +413,9 @@ class DeviceEngine:
                 self.W16_hi = torch.zeros((rows, self.ld16), dtype=torch.float16, device=self.dev)
                 self.W16_lo = torch.zeros((rows, self.ld16), dtype=torch.float16, device=self.dev) if need_lo else None
                 self.wnorm = torch.empty(rows, dtype=torch.float32, device=self.dev)
+                # wnorm as an MMA operand (dbgsom_prepare_bias): three fp16 pieces per shadow row, rest stays zero
+                self.Wb16 = torch.zeros((rows, 64), dtype=torch.float16, device=self.dev)
+                self.bias_scale = torch.zeros(1, dtype=torch.float32, device=self.dev)
         nat.check(
             self.lib.dbgsom_prepare_w(
                 W.data_ptr(), m, self.ldx, self.shift.data_ptr(), self.scale, self.W32.data_ptr(),
@@ -439,6 +442,19 @@ class DeviceEngine:
                 "dbgsom_exclude_duplicates",
             )
             self.launches += 2
+        # experiment, off by default: wnorm enters the accumulator through an extra k-step (dbgsom_prepare_bias).  It
+        # halves the epilogue's shared-memory loads but measured no gain (D = 256: MMA bound; D = 128: the epilogue is
+        # bound by its instruction count, not by the shared-memory pipe) -- see DESIGN.md, K1.
+        if tensor and need_lo and os.environ.get("DBGSOM_TC_BIAS", "0") == "1":
+            nat.check(
+                self.lib.dbgsom_prepare_bias(self.wnorm.data_ptr(), mpad, self.wmax.data_ptr(), self.Wb16.data_ptr(),
+                                             self.bias_scale.data_ptr(), self._stream()),
+                "dbgsom_prepare_bias",
+            )
+            self.launches += 1
+            self._bias_ready = True
+        else:
+            self._bias_ready = False
         return mpad
 
     def _run_bmu(self, X, n: int, ldx: int, x16, W, m: int, n_bmu: int, want_dist: bool, idx, dist, backend=None):
@@ -464,6 +480,8 @@ class DeviceEngine:
             a.d_W16_hi = self.W16_hi.data_ptr()
             a.d_W16_lo = self.W16_lo.data_ptr() if self.W16_lo is not None else None
             a.d_wnorm = self.wnorm.data_ptr()
+            if getattr(self, "_bias_ready", False):
+                a.d_Wb16, a.d_bias_scale = self.Wb16.data_ptr(), self.bias_scale.data_ptr()
             a.d_proto_of_col = self.proto_of_col.data_ptr()
             a.proto_stride = self.proto_stride
             a.ties_any = int(self._ties_any and n_bmu == 1)

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define DBGSOM_ABI_VERSION 5
+#define DBGSOM_ABI_VERSION 6
 
 #define DBGSOM_OK 0
 #define DBGSOM_E_BADARG (-1)      /* null pointer, non-positive size, bad enum             */
@@ -111,6 +111,15 @@ int dbgsom_prepare_w(const double* d_W, int M, int D, const float* d_shift, floa
 int dbgsom_exclude_duplicates(const double* d_W, int M, int D, const int32_t* d_col_of_proto /*[M..] or NULL*/,
                               float* d_wnorm, uint64_t* d_hash, void* stream);
 
+/* Optional, after dbgsom_prepare_w (and dbgsom_exclude_duplicates): wnorm as an MMA operand.  Writes three fp16
+ * pieces of -wnorm / (2 E) into the first three columns of d_Wb16[c, 0:64] (c = shadow row; the other columns must
+ * be zero and are not touched) and E, a power of two chosen from max |wnorm|, into d_bias_scale[0] (0 = the values
+ * do not fit fp16 pieces: the search then keeps loading wnorm).  With dbgsom_bmu_args.d_Wb16 / d_bias_scale set, the
+ * CTA-pair form of the tensor search ends every output tile with one extra k-step (A = E in three columns), so its
+ * epilogue reads scores straight from the accumulator. */
+int dbgsom_prepare_bias(const float* d_wnorm, int Mpad, const float* d_wmax, uint16_t* d_Wb16 /*[Mpad, 64]*/,
+                        float* d_bias_scale /*[1]*/, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * K1  best-matching-unit search
  * replaces  BaseSom._get_winning_neurons(data, n_bmu)   dbgsom/BaseSom.py:446-464
@@ -146,6 +155,8 @@ typedef struct dbgsom_bmu_args {
   const uint16_t* d_W16_hi; /* [Mpad, ld16]; may be NULL for DBGSOM_BMU_SIMT */
   const uint16_t* d_W16_lo; /* [Mpad, ld16]; needed for n_pass = 3 */
   const float* d_wnorm;    /* [Mpad]; may be NULL for DBGSOM_BMU_SIMT */
+  const uint16_t* d_Wb16;  /* [Mpad, 64] from dbgsom_prepare_bias, or NULL */
+  const float* d_bias_scale; /* [1] from dbgsom_prepare_bias, or NULL */
   const float* d_wmax;     /* [4] from dbgsom_prepare_w */
   const int32_t* d_proto_of_col; /* [Mpad] prototype index stored in shadow row c (tensor back end;
                               the inverse of the map given to dbgsom_prepare_w; entries >= M are padding) */

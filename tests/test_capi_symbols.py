@@ -57,7 +57,7 @@ def test_argument_errors_do_not_touch_the_gpu(lib):
 
 def test_struct_sizes_match_the_c_layout():
     # 64-bit layout of the three argument structs (guards against field drift in the binding)
-    assert ctypes.sizeof(nat.BmuArgs) == 208  # 42 x 4-byte-or-8-byte fields, see header
+    assert ctypes.sizeof(nat.BmuArgs) == 224
     assert ctypes.sizeof(nat.AccumulateArgs) == 112
     assert ctypes.sizeof(nat.SmoothArgs) == 96
 

@@ -724,9 +724,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         mbar_wait(&bars->tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t tmem_acc = tmem_base + lane_base + acc * BN;
+        // every fourth chunk (counted over the whole row tile) is mine: start at it instead of testing each one
 #pragma unroll 1
-        for (int c = 0; c < CHUNKS; ++c) {
-          if (((nt * CHUNKS + c) & (EPI_SUBS - 1)) != sub) continue;  // every fourth chunk is mine
+        for (int c = (sub - nt * CHUNKS) & (EPI_SUBS - 1); c < CHUNKS; c += EPI_SUBS) {
           uint32_t r[32];
           tmem_ld_32x32(tmem_acc + c * 32, r);
           const int col = nt * BN + c * 32;
@@ -742,21 +742,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           tmem_ld_wait();
           // pass A: smallest score(s) of the chunk
           float a1 = kInf, a2 = kInf;
+          float gm[8];  // minimum of each group of four columns: pass B re-examines only the groups in bound
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
             const float s0 = fmaf(-2.f, __uint_as_float(r[4 * g + 0]), w4[g].x);
             const float s1 = fmaf(-2.f, __uint_as_float(r[4 * g + 1]), w4[g].y);
             const float s2 = fmaf(-2.f, __uint_as_float(r[4 * g + 2]), w4[g].z);
             const float s3 = fmaf(-2.f, __uint_as_float(r[4 * g + 3]), w4[g].w);
+            gm[g] = fminf(fminf(s0, s1), fminf(s2, s3));
             if (NB == 2) {
               a2 = fminf(a2, fmaxf(a1, s0)); a1 = fminf(a1, s0);
               a2 = fminf(a2, fmaxf(a1, s1)); a1 = fminf(a1, s1);
               a2 = fminf(a2, fmaxf(a1, s2)); a1 = fminf(a1, s2);
               a2 = fminf(a2, fmaxf(a1, s3)); a1 = fminf(a1, s3);
-            } else {
-              a1 = fminf(fminf(a1, fminf(s0, s1)), fminf(s2, s3));
             }
           }
+          if (NB == 1) a1 = fminf(fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3])), fminf(fminf(gm[4], gm[5]), fminf(gm[6], gm[7])));
           // fold into the running minima; NB == 1 also shares the minimum with the other three
           // warps of this row (a racy read-modify-write is fine: every value written is a score that
           // was really seen, so the threshold can only be looser than necessary, never tighter)
@@ -786,10 +787,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
               uint32_t inb = 0;
 #pragma unroll
               for (int g = 0; g < 8; ++g) {
-                inb |= (fmaf(-2.f, __uint_as_float(r[4 * g + 0]), w4[g].x) <= thr ? 1u : 0u) << (4 * g + 0);
-                inb |= (fmaf(-2.f, __uint_as_float(r[4 * g + 1]), w4[g].y) <= thr ? 1u : 0u) << (4 * g + 1);
-                inb |= (fmaf(-2.f, __uint_as_float(r[4 * g + 2]), w4[g].z) <= thr ? 1u : 0u) << (4 * g + 2);
-                inb |= (fmaf(-2.f, __uint_as_float(r[4 * g + 3]), w4[g].w) <= thr ? 1u : 0u) << (4 * g + 3);
+                if (gm[g] <= thr) {  // usually one group per lane: the others cost a compare and a branch
+                  inb |= (fmaf(-2.f, __uint_as_float(r[4 * g + 0]), w4[g].x) <= thr ? 1u : 0u) << (4 * g + 0);
+                  inb |= (fmaf(-2.f, __uint_as_float(r[4 * g + 1]), w4[g].y) <= thr ? 1u : 0u) << (4 * g + 1);
+                  inb |= (fmaf(-2.f, __uint_as_float(r[4 * g + 2]), w4[g].z) <= thr ? 1u : 0u) << (4 * g + 2);
+                  inb |= (fmaf(-2.f, __uint_as_float(r[4 * g + 3]), w4[g].w) <= thr ? 1u : 0u) << (4 * g + 3);
+                }
               }
               if ((inb & (inb - 1)) == 0) {
                 if (inb) {

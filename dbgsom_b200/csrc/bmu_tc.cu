@@ -327,14 +327,16 @@ __device__ __noinline__ float2 slow_offer(float s, int col, uint32_t val_addr, u
 //      through the ring once per row tile and are moved with tcgen05.cp; the MMA then takes A from TMEM,
 //      which leaves all shared memory to the prototype ring (5 stages instead of 2 at D = 256, 3 passes)
 //      and, for D <= 128, tensor-memory room for three accumulator buffers instead of two.
-template <int NPASS, int BN, int RES_KB, int AKB>
+// PAIRS: the streamed-operand form run as CTA pairs -- each CTA stages only its half of a prototype tile
+template <int NPASS, int BN, int RES_KB, int AKB, bool PAIRS = false>
 struct Cfg {
   static constexpr bool ATM = AKB > 0;  // AKB: k-blocks of the sample tile held in tensor memory
   static constexpr bool XRES = RES_KB > 0;
   static constexpr bool ASTREAM = !XRES && !ATM;
   static constexpr int NA = NPASS == 3 ? 2 : 1;  // hi (+ lo) tiles per operand
   static constexpr int B_TILE_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = NA * B_TILE_BYTES + (ASTREAM ? NA * A_TILE_BYTES : 0);
+  static_assert(!PAIRS || ASTREAM, "PAIRS is the streamed form");
+  static constexpr int STAGE_BYTES = NA * (PAIRS ? B_TILE_BYTES / 2 : B_TILE_BYTES) + (ASTREAM ? NA * A_TILE_BYTES : 0);
   static_assert(!ATM || (RES_KB == 0 && B_TILE_BYTES == A_TILE_BYTES), "TMEM-resident A shares the ring: BN must be 128");
   static constexpr int A_COLS = AKB * NA * (BK / 2);                 // tensor-memory columns of the sample tile
   static constexpr int NACC = ATM ? ((512 - A_COLS) / BN > 4 ? 4 : (512 - A_COLS) / BN) : 2;  // accumulator buffers
@@ -378,16 +380,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                            const float* __restrict__ wmax, float bound_coef,
                            int32_t* __restrict__ idx_out, int32_t* __restrict__ cand_idx,
                            uint8_t* __restrict__ cand_count) {
-  using C = Cfg<NPASS, BN, RES_KB, AKB>;
+  using C = Cfg<NPASS, BN, RES_KB, AKB, PAIR && AKB == 0 && RES_KB == 0>;
   constexpr bool ATM = C::ATM;
-  static_assert(!PAIR || (ATM && CL == 2), "the CTA-pair form needs the sample tile in tensor memory and a cluster of two");
+  static_assert(!PAIR || (CL == 2 && (ATM || C::ASTREAM)), "the CTA-pair form needs a cluster of two; sample tile in tensor memory or streamed");
   constexpr int B_PART_BYTES = PAIR ? C::B_TILE_BYTES / 2 : C::B_TILE_BYTES;  // prototype tile bytes per CTA and shadow
   // pair: the ring is cut into 16 KB slots -- one k-block of one sample shadow, or one k-block of my half of both
   // prototype shadows -- so the same shared memory holds twice as many k-blocks in flight
-  constexpr int SLOT_BYTES = PAIR ? A_TILE_BYTES : C::STAGE_BYTES;
-  constexpr int NSLOT = PAIR ? (C::STAGES * C::STAGE_BYTES / A_TILE_BYTES > 16 ? 16 : C::STAGES * C::STAGE_BYTES / A_TILE_BYTES)
-                             : C::STAGES;
-  static_assert(!PAIR || C::NA * B_PART_BYTES <= SLOT_BYTES, "a prototype k-block of the pair form must fit a slot");
+  constexpr bool PAIR_ATM = PAIR && ATM;  // (the streamed pair form keeps whole stages: prototypes half + samples)
+  constexpr int SLOT_BYTES = PAIR_ATM ? A_TILE_BYTES : C::STAGE_BYTES;
+  constexpr int NSLOT = PAIR_ATM ? (C::STAGES * C::STAGE_BYTES / A_TILE_BYTES > 16 ? 16 : C::STAGES * C::STAGE_BYTES / A_TILE_BYTES)
+                                 : C::STAGES;
+  static_assert(!PAIR_ATM || C::NA * B_PART_BYTES <= SLOT_BYTES, "a prototype k-block of the pair form must fit a slot");
   constexpr int NACC = C::NACC;
   constexpr bool XRES = C::XRES;
   constexpr bool ASTREAM = C::ASTREAM;
@@ -519,11 +522,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             uint8_t* st = stages + stage * SLOT_BYTES;
             if (PAIR) {  // my half of the prototype tile (rows [rank * BN/2, +BN/2)) into MY shared memory only
               const uint32_t lead_full = mapa_u32(smem_u32(&bars->full[stage]), 0);
-              if (cl_rank == 0) mbar_expect_tx(&bars->full[stage], (uint32_t)(2 * C::NA * B_PART_BYTES));
+              if (cl_rank == 0) mbar_expect_tx(&bars->full[stage], (uint32_t)(2 * (C::NA * B_PART_BYTES + (ASTREAM ? C::NA * A_TILE_BYTES : 0))));
               else mbar_arrive_cluster(lead_full);
               const int prow = nt * BN + (int)cl_rank * (BN / 2);
               tma_load_2d_pair(st, &map_wh, lead_full, kb * BK, prow);
               if (NPASS == 3) tma_load_2d_pair(st + B_PART_BYTES, &map_wl, lead_full, kb * BK, prow);
+              if (ASTREAM) {  // my own sample rows, this k-block
+                uint8_t* sa = st + C::NA * B_PART_BYTES;
+                tma_load_2d_pair(sa, &map_xh, lead_full, kb * BK, row0);
+                if (NPASS == 3) tma_load_2d_pair(sa + A_TILE_BYTES, &map_xl, lead_full, kb * BK, row0);
+              }
               if (++stage == NSLOT) {
                 stage = 0;
                 phase ^= 1;
@@ -625,12 +633,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             const uint32_t b_hi = smem_u32(st);
             const uint32_t b_lo = b_hi + B_PART_BYTES;
             const uint32_t a_hi = XRES ? smem_u32(res_a + kb * C::NA * A_TILE_BYTES)
-                                       : smem_u32(st + C::NA * C::B_TILE_BYTES);
+                                       : smem_u32(st + C::NA * B_PART_BYTES);
             const uint32_t a_lo = a_hi + A_TILE_BYTES;
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint32_t koff = k * UMMA_K * 2;  // bytes along K inside the swizzle atom
-              if (PAIR) {
+              if (PAIR && ASTREAM) {  // both operands from shared memory, each CTA's own sample rows
+                tc_mma_f16_ss_pair(tmem_d, smem_desc_sw128(a_hi + koff), smem_desc_sw128(b_hi + koff), idesc, (kb | k) != 0);
+                if (NPASS == 3) {
+                  tc_mma_f16_ss_pair(tmem_d, smem_desc_sw128(a_hi + koff), smem_desc_sw128(b_lo + koff), idesc, 1);
+                  tc_mma_f16_ss_pair(tmem_d, smem_desc_sw128(a_lo + koff), smem_desc_sw128(b_hi + koff), idesc, 1);
+                }
+              } else if (PAIR) {
                 const uint32_t ta_hi = tmem_a + kb * (BK / 2) + k * 8;
                 const uint32_t ta_lo = ta_hi + AKB * (BK / 2);
                 tc_mma_f16_ts_pair(tmem_d, ta_hi, smem_desc_sw128(b_hi + koff), idesc, (kb | k) != 0);
@@ -960,7 +974,7 @@ int sm_count() {
 
 template <int NPASS, int NB, int BN, int RES_KB, int AKB, int CL, bool PAIR = false>
 int launch_cfg_cl(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t s) {
-  using C = Cfg<NPASS, BN, RES_KB, AKB>;
+  using C = Cfg<NPASS, BN, RES_KB, AKB, PAIR && AKB == 0 && RES_KB == 0>;
   CUtensorMap mxh, mxl, mwh, mwl;
   int rc = make_map(&mxh, a.d_X16_hi, a.N, a.ld16, BM);
   if (rc) return rc;
@@ -976,7 +990,7 @@ int launch_cfg_cl(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t
     mwl = mwh;
   }
   CUtensorMap mwb = mwh;
-  const bool with_bias = PAIR && a.d_Wb16 != nullptr && a.d_bias_scale != nullptr;
+  const bool with_bias = PAIR && C::ATM && a.d_Wb16 != nullptr && a.d_bias_scale != nullptr;
   if (with_bias) {
     rc = make_map(&mwb, a.d_Wb16, a.Mpad, BK, BN / CL);
     if (rc) return rc;
@@ -1076,6 +1090,11 @@ int launch_shape(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t 
     if (KB <= 2) return a_smem ? launch_cfg<NPASS, NB, 128, 2>(a, ws, s) : launch_cfg<NPASS, NB, 128, 0, 2>(a, ws, s);
     if (KB <= MAX_RES_KB)
       return a_smem ? launch_cfg<NPASS, NB, 128, 4>(a, ws, s) : launch_cfg<NPASS, NB, 128, 0, 4>(a, ws, s);
+    // D > 256: both operands stream.  As CTA pairs with 256-column MMAs each CTA stages its 128 sample rows and HALF
+    // of a 256-prototype tile per k-block (the single-CTA form wants 208 B/clk from the shared-memory pipe, this 104)
+    static const bool pairs = getenv("DBGSOM_TC_PAIR") == nullptr || atoi(getenv("DBGSOM_TC_PAIR")) != 0;
+    if (pairs && cluster_size() >= 2 && ceil_div<int64_t>(a.N, BM) >= sm_count())
+      return launch_cfg_cl<NPASS, NB, 256, 0, 0, 2, true>(a, ws, s);
     return launch_cfg<NPASS, NB, 128, 0>(a, ws, s);
   }
 }

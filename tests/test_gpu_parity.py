@@ -415,18 +415,25 @@ def test_fit_matches_reference_fixture(path):
         assert est.score(X, y) == pytest.approx(float(g["score"]), abs=2e-3)
 
 
-@pytest.mark.parametrize("env", [{"DBGSOM_TC_PAIR": "0"}, {"DBGSOM_TC_PAIR": "0", "DBGSOM_TC_CLUSTER": "1"},
-                                 {"DBGSOM_TC_PAIR": "1"}], ids=["multicast-cluster", "single-cta", "cta-pair"])
-def test_tensor_kernel_variants_agree_with_simt(env):
-    """The three forms of the tcgen05 candidate kernel (CTA pairs with cta_group::2 -- the default --, clusters
-    with TMA multicast, single CTAs) are selected by environment switches read once per process, so each runs
-    in its own interpreter: winners on a four-epoch bench-like trajectory must equal the fp32 SIMT back end's
+@pytest.mark.parametrize("env,shape", [
+    ({"DBGSOM_TC_PAIR": "0"}, ("60000", "256", "1024", "4")),
+    ({"DBGSOM_TC_PAIR": "0", "DBGSOM_TC_CLUSTER": "1"}, ("60000", "256", "1024", "4")),
+    ({"DBGSOM_TC_PAIR": "1"}, ("60000", "256", "1024", "4")),
+    ({"DBGSOM_TC_PAIR": "1", "DBGSOM_TC_BIAS": "1"}, ("60000", "128", "1024", "4")),
+    ({"DBGSOM_TC_PAIR": "1"}, ("60000", "512", "1024", "3")),
+    ({"DBGSOM_TC_PAIR": "0"}, ("60000", "512", "1024", "3")),
+], ids=["multicast-cluster", "single-cta", "cta-pair", "cta-pair-bias-kstep", "cta-pair-streamed", "multicast-streamed"])
+def test_tensor_kernel_variants_agree_with_simt(env, shape):
+    """The forms of the tcgen05 candidate kernel (CTA pairs with cta_group::2 -- the default; sample tile in tensor
+    memory for D <= 256, both operands streamed beyond; optionally wnorm as a bias k-step --, clusters with TMA
+    multicast, single CTAs) are selected by environment switches read once per process, so each runs in its own
+    interpreter: winners on a four-epoch bench-like trajectory must equal the fp32 SIMT back end's
     (both followed by the exact float64 re-score) outside a 1e-7 relative float64 gap."""
     import subprocess
     import sys
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, os.path.join(root, "tools", "check_backends.py"), "60000", "256", "1024", "4"],
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "check_backends.py"), *shape],
                          env={**os.environ, **env}, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert out.stdout.strip().endswith("OK"), out.stdout[-2000:]

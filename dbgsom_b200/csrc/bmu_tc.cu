@@ -9,13 +9,17 @@
 //   n_pass = 1 :  x'.u ~ xh.uh                          (fp16 inputs, error ~ 2^-9  ||x'|| ||u||)
 //   n_pass = 3 :  x'.u ~ xh.uh + xh.ul + xl.uh          (split fp16,  error ~ 2^-20 ||x'|| ||u||)
 // all products accumulate in one fp32 TMEM tile.  The epilogue never writes the N x M score
-// matrix: each of its 128 threads owns one TMEM lane = one sample row, streams the scores of all
-// M prototypes through RowTracker (common.cuh) and emits at most DBGSOM_MAX_CAND candidates per
-// sample for the exact float64 re-score (bmu_resolve.cu).
+// matrix: each of its threads owns one TMEM lane = one sample row, streams the scores of all M
+// prototypes through a small candidate table (gate / slow_offer below) and emits at most
+// DBGSOM_MAX_CAND candidates per sample for the exact float64 re-score (bmu_resolve.cu).
 //
 // CTA = 128 sample rows x all prototypes, persistent over row tiles.  Warp roles:
 //   warp 0      TMA producer (one elected lane)
-//   warp 1      MMA issuer   (one elected lane; tcgen05.mma cta_group::1, M=128, N=BN, K=16)
+//   warp 1      MMA issuer   (one elected lane).  Default: CTA PAIRS -- the leader CTA of a cluster of two
+//               issues tcgen05.mma.cta_group::2 (M = 256: 128 rows of each CTA; N = 128 with the sample tile
+//               in tensor memory for D <= 256, N = 256 with both operands streamed beyond), each CTA stages
+//               half of every prototype tile.  Otherwise cta_group::1, M = 128, optionally with the
+//               prototype tiles TMA-multicast to a cluster.
 //   warp 2      TMEM allocate / free
 //   warps 4-19  epilogue: tcgen05.ld 32x32b -> registers -> score -> candidate tracking.
 //               A warp can only read the 32 TMEM lanes of its scheduler quarter (warp % 4), so four
@@ -23,10 +27,10 @@
 //               scheduler runs at IPC ~0.06 (measured), four hide each other's latencies.  The four
 //               trackers of a row share their running minimum through shared memory and are merged
 //               at the end of the row tile.
-// Prototypes are visited in a fixed pseudo-random order (the shadow rows are permuted by
-// dbgsom_prepare_w): in map order a smooth map makes the scores fall monotonically towards the
-// best region, so nearly every chunk would set a new running minimum; in random order only
-// ~ln(#chunks) do.
+// Prototypes are visited in a fixed scattered order (the shadow rows are permuted by
+// dbgsom_prepare_w; shadow row c holds prototype (c * stride) % Mpad): in map order a smooth map makes
+// the scores fall monotonically towards the best region, so nearly every chunk would set a new
+// running minimum; in scattered order only ~ln(#chunks) do.
 // Pipelines: smem ring full/empty (TMA <-> MMA), TMEM double buffer full/empty (MMA <-> epilogue),
 // and, when the whole K extent of the sample tile fits (XRES), a resident A tile loaded once per
 // row tile so that only prototypes stream from L2.

@@ -23,6 +23,15 @@ from .hostmath import class_entropy, column_moments_to_stats
 _UPLOAD_ROWS = 1 << 20
 
 
+def scatter_stride(mpad: int) -> int:
+    """Stride of the shadow-row permutation: shadow row c holds prototype (c * stride) % mpad.  Close to
+    mpad / golden ratio (a low-discrepancy visiting order over the map) and coprime to mpad (a bijection)."""
+    stride = int(round(mpad * 0.6180339887498949)) | 1
+    while math.gcd(stride, mpad) != 1:
+        stride += 2
+    return stride
+
+
 def _round_up(a: int, b: int) -> int:
     return (a + b - 1) // b * b
 
@@ -393,9 +402,7 @@ class DeviceEngine:
                 # fixed scattered visiting order of the shadow rows (see bmu_tc.cu): shadow row c holds
                 # prototype (c * stride) % mpad, stride ~ mpad / golden ratio and coprime to mpad -- a
                 # low-discrepancy sequence over the map that the kernel can evaluate in registers
-                stride = int(round(mpad * 0.6180339887498949)) | 1
-                while math.gcd(stride, mpad) != 1:
-                    stride += 2
+                stride = scatter_stride(mpad)
                 self.proto_stride = stride if mpad <= 65535 else 0
                 proto_of_col = ((np.arange(mpad, dtype=np.int64) * stride) % mpad).astype(np.int32)
                 if os.environ.get("DBGSOM_PERM") == "random":  # tuning switch

@@ -74,3 +74,20 @@ def test_row_ops_reference_extrapolation_and_overwrite():
     t.error[4] = 3.0
     assert t.place((0, -1), epoch=9) == 4
     assert t.error[4] == 0.0 and t.epoch_created[4] == 9 and len(t) == 5
+
+
+def test_shadow_row_permutation_is_a_bijection():
+    """engine.scatter_stride: (c * stride) % mpad must visit every shadow row once (the candidate kernel evaluates
+    this formula in registers, dbgsom_bmu_args.proto_stride) and scatter neighbouring rows across the map."""
+    import numpy as np
+
+    from dbgsom_b200.engine import scatter_stride
+
+    for mpad in (256, 512, 768, 1024, 4096, 5120, 16384, 24576, 65280):
+        s = scatter_stride(mpad)
+        assert 0 < s < mpad
+        proto = (np.arange(mpad, dtype=np.int64) * s) % mpad
+        assert np.array_equal(np.sort(proto), np.arange(mpad))
+        assert int(mpad) * s < 2**32  # the kernel multiplies in 32 bits
+        # consecutive shadow rows are far apart on the map
+        assert np.abs(np.diff(proto)).min() > mpad // 4

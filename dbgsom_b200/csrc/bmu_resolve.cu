@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) bmu_resolve_kernel(
     const int32_t* __restrict__ cand_idx, const uint8_t* __restrict__ cand_count, int want_dist,
     int32_t* __restrict__ idx_out, double* __restrict__ dist_out, unsigned long long* __restrict__ stats,
     // flagged-sample policy (tensor back end only; xnorm16 == nullptr disables the shortcut)
-    const float* __restrict__ xnorm16, const float* __restrict__ wmax, float bound_coef, float inv_scale2,
+    const float* __restrict__ xnorm16, const float* __restrict__ wmax, float bound_coef, float acc_coef, float inv_scale2,
     float tie_rel, int32_t* __restrict__ rescan_count, int32_t* __restrict__ rescan_rows) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) bmu_resolve_kernel(
           // dbgsom_b200.h); the candidate search leaves s2 - s1 in the row's first candidate slot.
           const int jb = idx_out[row];
           const double db = sqdist_f64(x, W + (int64_t)jb * D, D, lane);
-          const double bound = (double)(tensor_score_bound(xnorm16[row], wmax, bound_coef) * inv_scale2);
+          const double bound = (double)(tensor_score_bound(xnorm16[row], wmax, bound_coef, acc_coef) * inv_scale2);
           const double gap = (double)(__int_as_float(cand_idx[row * kMaxCand]) * inv_scale2) + 2.0 * bound;
           if (jb >= 0 && gap <= (double)tie_rel * (db - 2.0 * bound)) {
             top.offer(db, jb);
@@ -253,6 +253,7 @@ int launch_bmu_resolve(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStr
   const bool shortcut = a.backend == DBGSOM_BMU_TENSOR && !a.strict;
   const float* xn = shortcut ? a.d_xnorm16 : nullptr;
   const float coef = tensor_bound_coef(a.n_pass, a.bound_scale);
+  const float acc_coef = tensor_acc_coef(a.n_pass, a.ld16, a.strict);
   const float inv_s2 = a.scale > 0.f ? 1.f / (a.scale * a.scale) : 1.f;
   const float tie = a.tie_rel > 0.f ? a.tie_rel : 1e-6f;
   DBGSOM_CUDA_TRY(cudaMemsetAsync(ws.rescan_count, 0, sizeof(int32_t), s));
@@ -260,13 +261,13 @@ int launch_bmu_resolve(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStr
   if (a.n_bmu == 1) {
     bmu_resolve_kernel<1><<<(unsigned)blocks, WARPS_PER_BLOCK * 32, 0, s>>>(
         a.d_X, a.N, a.D, a.ldx, a.d_W, a.M, ws.cand_idx, ws.cand_count, a.want_dist, a.d_idx, a.d_dist, stats, xn,
-        a.d_wmax, coef, inv_s2, tie, ws.rescan_count, ws.rescan_rows);
+        a.d_wmax, coef, acc_coef, inv_s2, tie, ws.rescan_count, ws.rescan_rows);
     DBGSOM_LAUNCH_CHECK();
     return wide ? launch_rescan<1, 4>(a, ws, s) : launch_rescan<1, 8>(a, ws, s);
   }
   bmu_resolve_kernel<2><<<(unsigned)blocks, WARPS_PER_BLOCK * 32, 0, s>>>(
       a.d_X, a.N, a.D, a.ldx, a.d_W, a.M, ws.cand_idx, ws.cand_count, a.want_dist, a.d_idx, a.d_dist, stats, xn,
-      a.d_wmax, coef, inv_s2, tie, ws.rescan_count, ws.rescan_rows);
+      a.d_wmax, coef, acc_coef, inv_s2, tie, ws.rescan_count, ws.rescan_rows);
   DBGSOM_LAUNCH_CHECK();
   return wide ? launch_rescan<2, 4>(a, ws, s) : launch_rescan<2, 8>(a, ws, s);
 }

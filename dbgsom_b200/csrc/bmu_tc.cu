@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                            int64_t N, int KB, int NT, const float* __restrict__ wnorm,
                            const int32_t* __restrict__ proto_of_col, int pstride, int ties_any,
                            const float* __restrict__ xnorm16,
-                           const float* __restrict__ wmax, float bound_coef,
+                           const float* __restrict__ wmax, float bound_coef, float acc_coef,
                            int32_t* __restrict__ idx_out, int32_t* __restrict__ cand_idx,
                            uint8_t* __restrict__ cand_count) {
   using C = Cfg<NPASS, BN, RES_KB, AKB, PAIR && AKB == 0 && RES_KB == 0>;
@@ -733,7 +733,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     uint32_t acc = 0, acc_phase = 0;
     for (int64_t it = 0; it < n_iters; ++it) {
       const int64_t row = tile_of(it) * BM + t;
-      const float tau = row < N ? 2.f * tensor_score_bound(xnorm16[row], wmax, bound_coef) : 0.f;
+      const float tau = row < N ? 2.f * tensor_score_bound(xnorm16[row], wmax, bound_coef, acc_coef) : 0.f;
       float m1 = kInf, m2 = kInf, thr = kInf, evicted = __int_as_float(0x7f800000);
       float gate = __int_as_float(0x7f800000);  // fast gate of my table (see slow_offer); +inf while a slot is free
       asm volatile("st.shared.v4.f32 [%0], {%1,%1,%1,%1};" ::"r"(my_val_addr), "f"(gate) : "memory");
@@ -1040,11 +1040,12 @@ int launch_cfg_cl(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t
   if (grid > max_grid) grid = max_grid;
   cfg.gridDim = dim3((unsigned)grid);
   const float coef = tensor_bound_coef(NPASS, a.bound_scale);
+  const float acc_coef = tensor_acc_coef(NPASS, a.ld16, a.strict);
   // the arithmetic form needs c * stride < 2^32 for every shadow row c
   const int pstride = a.proto_stride > 0 && a.Mpad <= 65535 && a.proto_stride < a.Mpad ? a.proto_stride : 0;
   DBGSOM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, mxh, mxl, mwh, mwl, mwb, with_bias ? a.d_bias_scale : (const float*)nullptr,
                                      a.N, KB, NT, a.d_wnorm, a.d_proto_of_col, pstride,
-                                     a.n_bmu == 1 ? a.ties_any : 0, a.d_xnorm16, a.d_wmax, coef, a.d_idx, ws.cand_idx, ws.cand_count));
+                                     a.n_bmu == 1 ? a.ties_any : 0, a.d_xnorm16, a.d_wmax, coef, acc_coef, a.d_idx, ws.cand_idx, ws.cand_count));
   DBGSOM_LAUNCH_CHECK();
   return DBGSOM_OK;
 }

@@ -5,6 +5,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cmath>
+#include <cstdlib>
+
 #include "../../include/dbgsom_b200.h"
 
 #define DBGSOM_CUDA_TRY(expr)                  \
@@ -206,9 +209,24 @@ struct RowTracker {
 // training trajectories): one pass  0.25   * 2^-9   (first wrong winners appear at ~0.03 * 2^-9),
 //                         three     0.0625 * 2^-19  (none seen down to 0.004 * 2^-19).
 // bound_scale = 1 selects the worst-case coefficient.
-__device__ __forceinline__ float tensor_score_bound(float xnorm, const float* __restrict__ wmax, float coef) {
+// The accumulation term grows with the length of the fp32 accumulation chain in tensor memory (one step per MMA
+// of 16 products): 2.4e-7 was calibrated at D = 256, three passes (48 steps).  Measured with
+// tools/check_backends.py at D = 4096 (768 steps; 150k rows x 1024 prototypes x 3 epochs, winners against the fp32
+// SIMT search and exact float64 scores): 9 wrong winners with exact relative gaps up to 8e-6 at 1x, 5 at 2x, none
+// at 4x and beyond.  Default: scaled with the SQUARE ROOT of the chain length (4x at D = 4096) -- the largest
+// factor at which flagged rows can still be proven near-ties; from ~6x every flagged row of a collapsed map goes
+// to the float64 re-scan (1 s per epoch at 200k x 4096 x 16384).  strict != 0 scales LINEARLY (16x at D = 4096): a
+// 4x margin over the smallest factor without wrong winners, at that price.  The real fix for D > 256 is a
+// shorter chain (partial accumulators summed in the epilogue): DESIGN.md section 8.
+__device__ __forceinline__ float tensor_score_bound(float xnorm, const float* __restrict__ wmax, float coef, float acc_coef) {
   const float xw = xnorm * wmax[0];
-  return xw * coef + 2.4e-7f * (xw + wmax[2]);
+  return xw * coef + acc_coef * (xw + wmax[2]);
+}
+inline float tensor_acc_coef(int n_pass, int64_t ld16, int strict) {
+  const double steps = (double)(ld16 / 16) * (n_pass == 3 ? 3.0 : 1.0);
+  double c = 2.4e-7 * (steps > 48.0 ? (strict ? steps / 48.0 : sqrt(steps / 48.0)) : 1.0);
+  if (const char* e = getenv("DBGSOM_ACC_SCALE")) c *= atof(e);  // calibration switch
+  return (float)c;
 }
 __host__ __device__ inline float tensor_bound_coef(int n_pass, float bound_scale) {
   if (n_pass == 1) return (bound_scale > 0.f ? bound_scale : 0.25f) * 1.953125e-3f;

@@ -177,7 +177,9 @@ typedef struct dbgsom_bmu_args {
                               (Cauchy-Schwarz) bound; <= 0 selects the calibrated default (0.25 for
                               one pass, 0.0625 for three, see csrc/common.cuh) */
   float tie_rel;           /* see above; <= 0 selects 1e-6 */
-  int32_t strict;          /* 1: flagged samples are always re-scored against all prototypes */
+  int32_t strict;          /* 1: flagged samples are always re-scored against all prototypes, and the fp32
+                              accumulation term of the tensor bound grows linearly (default: with the square
+                              root) with the accumulation chain for D > 256 (csrc/common.cuh tensor_acc_coef) */
   int32_t want_dist;       /* 0: winners only (training epoch); 1: also exact distances */
   /* outputs */
   int32_t* d_idx;          /* [N, n_bmu] winners, ascending distance */

@@ -50,6 +50,15 @@ def main():
             db = ((xs - Wd[ref[diff, 0].long()]) ** 2).sum(1)
             rel = (da - db).abs() / torch.minimum(da, db).clamp_min(1e-300)
             bad = int((rel > 1e-7).sum())
+            if bad:  # who is right?  exact float64 scores of the differing rows against every prototype
+                sel = diff[rel > 1e-7][:8]
+                xs8 = eng.X[sel][:, :d].double()
+                d2 = ((xs8[:, None, :] - Wd[None, :, :]) ** 2).sum(2)
+                best = d2.argmin(1)
+                two = torch.topk(d2, 2, dim=1, largest=False).values
+                for q in range(sel.numel()):
+                    print(f"   row {int(sel[q])}: exact {int(best[q])} tensor {int(got[sel[q], 0])} simt {int(ref[sel[q], 0])} "
+                          f"exact rel gap {float((two[q, 1] - two[q, 0]) / two[q, 0]):.3e}", flush=True)
         total_bad += bad
         print(f"epoch {e}: {int(diff.numel())} rows differ, {bad} of them beyond a 1e-7 relative gap; min idx {int(got.min())}", flush=True)
         eng.epoch(sigma_at(e, m), True, False)

@@ -148,7 +148,10 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) bmu_resolve_kernel(
 // and were a third of the kernel's instructions); lane (r * RS_P + p) * 32 / (R * RS_P) then owns the
 // pair (sample r, prototype j0 + p) and keeps its own running top-2.
 constexpr int RS_P = 4;
-template <int NB, int R>
+// XT: element type of the staged samples.  double for D <= 3200; float beyond (converted per use on the otherwise
+// idle conversion unit), which keeps R = 8 samples per pass over the prototypes within shared memory -- with 16384 x
+// 4096 float64 prototypes the pass is bound by L2 bandwidth, so rows per pass is what counts.
+template <int NB, int R, typename XT>
 __global__ void __launch_bounds__(256) bmu_rescan_kernel(const float* __restrict__ X, int64_t ldx, int D,
                                                         const double* __restrict__ W, int M,
                                                         const int32_t* __restrict__ rescan_count,
@@ -156,7 +159,8 @@ __global__ void __launch_bounds__(256) bmu_rescan_kernel(const float* __restrict
                                                         int32_t* __restrict__ idx_out, double* __restrict__ dist_out) {
   constexpr int V = R * RS_P;   // values per lane; 32 / V lanes end up holding each total
   static_assert(V <= 32 && 32 % V == 0, "R * RS_P must divide the warp");
-  extern __shared__ __align__(16) double xs[];  // [R][D]
+  extern __shared__ __align__(16) unsigned char xs_raw[];
+  XT* xs = reinterpret_cast<XT*>(xs_raw);  // [R][D]
   __shared__ double m_d[8][V][2];
   __shared__ int m_i[8][V][2];
   __shared__ int row_id[R];
@@ -176,7 +180,7 @@ __global__ void __launch_bounds__(256) bmu_rescan_kernel(const float* __restrict
     for (int e = threadIdx.x; e < R * D; e += 256) {
       const int r = e / D, d = e % D;
       const int rid = row_id[r];
-      xs[e] = rid >= 0 ? (double)X[(int64_t)rid * ldx + d] : 0.0;
+      xs[e] = rid >= 0 ? (XT)X[(int64_t)rid * ldx + d] : (XT)0;
     }
     __syncthreads();
     Top2 mine;
@@ -194,7 +198,13 @@ __global__ void __launch_bounds__(256) bmu_rescan_kernel(const float* __restrict
         }
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          const double2 xv = *reinterpret_cast<const double2*>(xs + r * D + d);
+          double2 xv;
+          if constexpr (sizeof(XT) == 8) {
+            xv = *reinterpret_cast<const double2*>(xs + r * D + d);
+          } else {
+            const float2 xf = *reinterpret_cast<const float2*>(xs + r * D + d);
+            xv = make_double2((double)xf.x, (double)xf.y);
+          }
 #pragma unroll
           for (int p = 0; p < RS_P; ++p) {
             const double a = xv.x - w[p].x, b = xv.y - w[p].y;
@@ -232,10 +242,10 @@ __global__ void __launch_bounds__(256) bmu_rescan_kernel(const float* __restrict
   }
 }
 
-template <int NB, int R>
+template <int NB, int R, typename XT>
 int launch_rescan(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t s) {
-  const size_t smem = (size_t)R * a.D * sizeof(double);
-  auto kern = bmu_rescan_kernel<NB, R>;
+  const size_t smem = (size_t)R * a.D * sizeof(XT);
+  auto kern = bmu_rescan_kernel<NB, R, XT>;
   DBGSOM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int per_sm = smem > 100 * 1024 ? 1 : 2;
   kern<<<148 * per_sm, 256, smem, s>>>(a.d_X, a.ldx, a.D, a.d_W, a.M, ws.rescan_count, ws.rescan_rows, a.want_dist,
@@ -257,19 +267,19 @@ int launch_bmu_resolve(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStr
   const float inv_s2 = a.scale > 0.f ? 1.f / (a.scale * a.scale) : 1.f;
   const float tie = a.tie_rel > 0.f ? a.tie_rel : 1e-6f;
   DBGSOM_CUDA_TRY(cudaMemsetAsync(ws.rescan_count, 0, sizeof(int32_t), s));
-  const bool wide = (size_t)8 * a.D * sizeof(double) > 200 * 1024;  // D > 3200: four samples per CTA
+  const bool wide = (size_t)8 * a.D * sizeof(double) > 200 * 1024;  // D > 3200: samples staged as float
   if (a.n_bmu == 1) {
     bmu_resolve_kernel<1><<<(unsigned)blocks, WARPS_PER_BLOCK * 32, 0, s>>>(
         a.d_X, a.N, a.D, a.ldx, a.d_W, a.M, ws.cand_idx, ws.cand_count, a.want_dist, a.d_idx, a.d_dist, stats, xn,
         a.d_wmax, coef, acc_coef, inv_s2, tie, ws.rescan_count, ws.rescan_rows);
     DBGSOM_LAUNCH_CHECK();
-    return wide ? launch_rescan<1, 4>(a, ws, s) : launch_rescan<1, 8>(a, ws, s);
+    return wide ? launch_rescan<1, 8, float>(a, ws, s) : launch_rescan<1, 8, double>(a, ws, s);
   }
   bmu_resolve_kernel<2><<<(unsigned)blocks, WARPS_PER_BLOCK * 32, 0, s>>>(
       a.d_X, a.N, a.D, a.ldx, a.d_W, a.M, ws.cand_idx, ws.cand_count, a.want_dist, a.d_idx, a.d_dist, stats, xn,
       a.d_wmax, coef, acc_coef, inv_s2, tie, ws.rescan_count, ws.rescan_rows);
   DBGSOM_LAUNCH_CHECK();
-  return wide ? launch_rescan<2, 4>(a, ws, s) : launch_rescan<2, 8>(a, ws, s);
+  return wide ? launch_rescan<2, 8, float>(a, ws, s) : launch_rescan<2, 8, double>(a, ws, s);
 }
 
 }  // namespace dbgsom

@@ -263,7 +263,7 @@ int launch_bmu_resolve(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStr
   const bool shortcut = a.backend == DBGSOM_BMU_TENSOR && !a.strict;
   const float* xn = shortcut ? a.d_xnorm16 : nullptr;
   const float coef = tensor_bound_coef(a.n_pass, a.bound_scale);
-  const float acc_coef = tensor_acc_coef(a.n_pass, a.ld16, a.strict);
+  const float acc_coef = tensor_acc_coef_args(a);
   const float inv_s2 = a.scale > 0.f ? 1.f / (a.scale * a.scale) : 1.f;
   const float tie = a.tie_rel > 0.f ? a.tie_rel : 1e-6f;
   DBGSOM_CUDA_TRY(cudaMemsetAsync(ws.rescan_count, 0, sizeof(int32_t), s));

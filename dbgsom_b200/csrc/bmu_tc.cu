@@ -343,7 +343,9 @@ struct Cfg {
   static constexpr int STAGE_BYTES = NA * (PAIRS ? B_TILE_BYTES / 2 : B_TILE_BYTES) + (ASTREAM ? NA * A_TILE_BYTES : 0);
   static_assert(!ATM || (RES_KB == 0 && B_TILE_BYTES == A_TILE_BYTES), "TMEM-resident A shares the ring: BN must be 128");
   static constexpr int A_COLS = AKB * NA * (BK / 2);                 // tensor-memory columns of the sample tile
-  static constexpr int NACC = ATM ? ((512 - A_COLS) / BN > 4 ? 4 : (512 - A_COLS) / BN) : 2;  // accumulator buffers
+  // accumulator buffers; the streamed pair form with 128-column tiles closes its accumulation chain every few
+  // k-blocks (SEGM in the kernel) and rotates through four partial accumulators
+  static constexpr int NACC = ATM ? ((512 - A_COLS) / BN > 4 ? 4 : (512 - A_COLS) / BN) : (PAIRS && BN == 128 ? 4 : 2);
   static_assert(NACC >= 2, "need two accumulator buffers");
   static constexpr int RES_BYTES = RES_KB * NA * A_TILE_BYTES;
   // candidate tables [row][sub][KSUB] (idx + val), shared running minima [row], merge states [row][sub][4]
@@ -355,7 +357,7 @@ struct Cfg {
   static constexpr int STAGES_RAW = (SMEM_BUDGET - RES_BYTES - RING_BYTES - MISC_BYTES - WN_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int SMEM_BYTES = RES_BYTES + STAGES * STAGE_BYTES + RING_BYTES + MISC_BYTES + WN_BYTES + 1024;
-  static constexpr int TMEM_COLS = ATM ? 512 : 2 * BN;  // accumulator buffers (+ the sample tile)
+  static constexpr int TMEM_COLS = ATM ? 512 : NACC * BN;  // accumulator buffers (+ the sample tile)
   static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
 };
 
@@ -390,6 +392,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   constexpr int B_PART_BYTES = PAIR ? C::B_TILE_BYTES / 2 : C::B_TILE_BYTES;  // prototype tile bytes per CTA and shadow
   // pair: the ring is cut into 16 KB slots -- one k-block of one sample shadow, or one k-block of my half of both
   // prototype shadows -- so the same shared memory holds twice as many k-blocks in flight
+  // SEGM: segmented accumulation (streamed pair form, 128-column tiles).  The fp32 accumulator in tensor memory takes
+  // one rounding per MMA, 768 of them per score at D = 4096, and the error bound had to grow with that chain
+  // (common.cuh, tensor_acc_coef).  Here the MMA stream starts a fresh accumulator every SEG k-blocks (48 steps, the
+  // chain of D = 256) and the epilogue sums the partial tiles in registers, so the bound of D = 256 (x2 for the
+  // fp32 sums) holds for any D.
+  constexpr bool SEGM = PAIR && C::ASTREAM && BN == 128;
+  constexpr int SEG = 4;
+  static_assert(!SEGM || BN / 32 == EPI_SUBS, "segmented accumulation: one chunk per epilogue warp and tile");
   constexpr bool PAIR_ATM = PAIR && ATM;  // (the streamed pair form keeps whole stages: prototypes half + samples)
   constexpr int SLOT_BYTES = PAIR_ATM ? A_TILE_BYTES : C::STAGE_BYTES;
   constexpr int NSLOT = PAIR_ATM ? (C::STAGES * C::STAGE_BYTES / A_TILE_BYTES > 16 ? 16 : C::STAGES * C::STAGE_BYTES / A_TILE_BYTES)
@@ -627,10 +637,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           }
         }
         for (int nt = 0; nt < NT; ++nt) {
-          mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
-          tc_fence_after();
-          const uint32_t tmem_d = tmem_base + acc * BN;
+          uint32_t tmem_d = tmem_base + acc * BN;
+          if (!SEGM) {
+            mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
+            tc_fence_after();
+          }
           for (int kb = 0; kb < KB; ++kb) {
+            if (SEGM && kb % SEG == 0) {  // a fresh partial accumulator
+              mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
+              tc_fence_after();
+              tmem_d = tmem_base + acc * BN;
+            }
             mbar_wait(&bars->full[stage], phase);
             tc_fence_after();
             uint8_t* st = stages + stage * SLOT_BYTES;
@@ -643,7 +660,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint32_t koff = k * UMMA_K * 2;  // bytes along K inside the swizzle atom
               if (PAIR && ASTREAM) {  // both operands from shared memory, each CTA's own sample rows
-                tc_mma_f16_ss_pair(tmem_d, smem_desc_sw128(a_hi + koff), smem_desc_sw128(b_hi + koff), idesc, (kb | k) != 0);
+                tc_mma_f16_ss_pair(tmem_d, smem_desc_sw128(a_hi + koff), smem_desc_sw128(b_hi + koff), idesc,
+                                   ((SEGM ? kb % SEG : kb) | k) != 0);
                 if (NPASS == 3) {
                   tc_mma_f16_ss_pair(tmem_d, smem_desc_sw128(a_hi + koff), smem_desc_sw128(b_lo + koff), idesc, 1);
                   tc_mma_f16_ss_pair(tmem_d, smem_desc_sw128(a_lo + koff), smem_desc_sw128(b_hi + koff), idesc, 1);
@@ -678,6 +696,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             if (++stage == NSLOT) {
               stage = 0;
               phase ^= 1;
+            }
+            if (SEGM && kb % SEG == SEG - 1 && kb != KB - 1) {  // partial accumulator complete (the last one below)
+              tc_commit_pair(&bars->tmem_full[acc], cl_mask);
+              if (++acc == NACC) {
+                acc = 0;
+                acc_phase ^= 1;
+              }
             }
           }
           if (PAIR && bias_mode) {  // + E * (h + m + l) = -wnorm / 2: the accumulator is now -score / 2
@@ -746,7 +771,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll 1
         for (int c = (sub - nt * CHUNKS) & (EPI_SUBS - 1); c < CHUNKS; c += EPI_SUBS) {
           uint32_t r[32];
-          tmem_ld_32x32(tmem_acc + c * 32, r);
+          if (SEGM) {
+            // my chunk of every partial accumulator of this tile, summed in fp32 registers; a partial buffer goes back
+            // to the MMA stream as soon as it is read (the last one is released below like an ordinary accumulator)
+            float sum[32];
+            const int nseg = (KB + SEG - 1) / SEG;
+            for (int seg = 0; seg < nseg; ++seg) {
+              if (seg > 0) {
+                mbar_wait(&bars->tmem_full[acc], acc_phase);
+                tc_fence_after();
+              }
+              tmem_ld_32x32(tmem_base + lane_base + acc * BN + c * 32, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 32; ++e) sum[e] = seg == 0 ? __uint_as_float(r[e]) : sum[e] + __uint_as_float(r[e]);
+              if (seg < nseg - 1) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->tmem_empty[acc]), 0));
+                if (++acc == NACC) {
+                  acc = 0;
+                  acc_phase ^= 1;
+                }
+              }
+            }
+#pragma unroll
+            for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(sum[e]);
+          } else {
+            tmem_ld_32x32(tmem_acc + c * 32, r);
+          }
           const int col = nt * BN + c * 32;
           const float4* wn4 = reinterpret_cast<const float4*>(wn_src + col);
           float4 w4[8];
@@ -1040,7 +1093,7 @@ int launch_cfg_cl(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t
   if (grid > max_grid) grid = max_grid;
   cfg.gridDim = dim3((unsigned)grid);
   const float coef = tensor_bound_coef(NPASS, a.bound_scale);
-  const float acc_coef = tensor_acc_coef(NPASS, a.ld16, a.strict);
+  const float acc_coef = tensor_acc_coef_args(a);
   // the arithmetic form needs c * stride < 2^32 for every shadow row c
   const int pstride = a.proto_stride > 0 && a.Mpad <= 65535 && a.proto_stride < a.Mpad ? a.proto_stride : 0;
   DBGSOM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, mxh, mxl, mwh, mwl, mwb, with_bias ? a.d_bias_scale : (const float*)nullptr,
@@ -1081,6 +1134,18 @@ int launch_cfg(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t s)
   return launch_cfg_cl<NPASS, NB, BN, RES_KB, AKB, 1>(a, ws, s);
 }
 
+// which form runs for D > 256 (three passes): the decisions are functions of the arguments so that the re-score
+// (bmu_resolve.cu) can use the error bound of the form that produced the candidates
+bool streamed_pairs(const dbgsom_bmu_args& a) {
+  static const bool pairs = getenv("DBGSOM_TC_PAIR") == nullptr || atoi(getenv("DBGSOM_TC_PAIR")) != 0;
+  return a.backend == DBGSOM_BMU_TENSOR && a.n_pass == 3 && a.ld16 / BK > MAX_RES_KB && pairs && cluster_size() >= 2 &&
+         ceil_div<int64_t>(a.N, BM) >= sm_count();
+}
+bool streamed_segmented(const dbgsom_bmu_args& a) {
+  static const bool segm = getenv("DBGSOM_TC_SEGM") == nullptr || atoi(getenv("DBGSOM_TC_SEGM")) != 0;
+  return segm && streamed_pairs(a);
+}
+
 template <int NPASS, int NB>
 int launch_shape(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t s) {
   // Tile shapes by shared-memory budget (227 KB): the resident sample tile takes 16 KB per k-block
@@ -1097,14 +1162,26 @@ int launch_shape(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t 
       return a_smem ? launch_cfg<NPASS, NB, 128, 4>(a, ws, s) : launch_cfg<NPASS, NB, 128, 0, 4>(a, ws, s);
     // D > 256: both operands stream.  As CTA pairs with 256-column MMAs each CTA stages its 128 sample rows and HALF
     // of a 256-prototype tile per k-block (the single-CTA form wants 208 B/clk from the shared-memory pipe, this 104)
-    static const bool pairs = getenv("DBGSOM_TC_PAIR") == nullptr || atoi(getenv("DBGSOM_TC_PAIR")) != 0;
-    if (pairs && cluster_size() >= 2 && ceil_div<int64_t>(a.N, BM) >= sm_count())
+    if (streamed_pairs(a)) {
+      // segmented accumulation (128-column tiles, partial accumulators summed in the epilogue) keeps the error bound
+      // of D = 256 at any D; DBGSOM_TC_SEGM=0 selects the one-chain form with 256-column tiles
+      if (streamed_segmented(a)) return launch_cfg_cl<NPASS, NB, 128, 0, 0, 2, true>(a, ws, s);
       return launch_cfg_cl<NPASS, NB, 256, 0, 0, 2, true>(a, ws, s);
+    }
     return launch_cfg<NPASS, NB, 128, 0>(a, ws, s);
   }
 }
 
 }  // namespace
+
+float tensor_acc_coef_args(const dbgsom_bmu_args& a) {
+  if (streamed_segmented(a)) {  // chains of 48 steps like D = 256, plus the fp32 sums of the partial tiles
+    double c = 2.4e-7 * (a.strict ? 4.0 : 2.0);
+    if (const char* e = getenv("DBGSOM_ACC_SCALE")) c *= atof(e);
+    return (float)c;
+  }
+  return tensor_acc_coef(a.n_pass, a.ld16, a.strict);
+}
 
 int launch_bmu_cand_tensor(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t s) {
   if (a.ld16 % BK != 0 || a.Mpad % 256 != 0 || a.Mpad < a.M) return DBGSOM_E_UNSUPPORTED;

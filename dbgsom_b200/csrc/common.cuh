@@ -216,8 +216,9 @@ struct RowTracker {
 // at 4x and beyond.  Default: scaled with the SQUARE ROOT of the chain length (4x at D = 4096) -- the largest
 // factor at which flagged rows can still be proven near-ties; from ~6x every flagged row of a collapsed map goes
 // to the float64 re-scan (1 s per epoch at 200k x 4096 x 16384).  strict != 0 scales LINEARLY (16x at D = 4096): a
-// 4x margin over the smallest factor without wrong winners, at that price.  The real fix for D > 256 is a
-// shorter chain (partial accumulators summed in the epilogue): DESIGN.md section 8.
+// 4x margin over the smallest factor without wrong winners, at that price.  The streamed CTA-pair form avoids
+// all this by cutting the chain (segmented accumulation, bmu_tc.cu: tensor_acc_coef_args); this function serves
+// the one-chain forms.
 __device__ __forceinline__ float tensor_score_bound(float xnorm, const float* __restrict__ wmax, float coef, float acc_coef) {
   const float xw = xnorm * wmax[0];
   return xw * coef + acc_coef * (xw + wmax[2]);
@@ -228,6 +229,8 @@ inline float tensor_acc_coef(int n_pass, int64_t ld16, int strict) {
   if (const char* e = getenv("DBGSOM_ACC_SCALE")) c *= atof(e);  // calibration switch
   return (float)c;
 }
+// accumulation coefficient of the kernel form that runs for these arguments (bmu_tc.cu)
+float tensor_acc_coef_args(const dbgsom_bmu_args& a);
 __host__ __device__ inline float tensor_bound_coef(int n_pass, float bound_scale) {
   if (n_pass == 1) return (bound_scale > 0.f ? bound_scale : 0.25f) * 1.953125e-3f;
   return (bound_scale > 0.f ? bound_scale : 0.0625f) * 1.9073486e-6f;

@@ -421,12 +421,13 @@ def test_fit_matches_reference_fixture(path):
     ({"DBGSOM_TC_PAIR": "1"}, ("60000", "256", "1024", "4")),
     ({"DBGSOM_TC_PAIR": "1", "DBGSOM_TC_BIAS": "1"}, ("60000", "128", "1024", "4")),
     ({"DBGSOM_TC_PAIR": "1"}, ("60000", "512", "1024", "3")),
+    ({"DBGSOM_TC_PAIR": "1", "DBGSOM_TC_SEGM": "0"}, ("60000", "512", "1024", "3")),
     ({"DBGSOM_TC_PAIR": "0"}, ("60000", "512", "1024", "3")),
-    # 768 accumulation steps per score: the error bound has to grow with the chain (wrong winners with exact
-    # relative gaps up to 8e-6 before tensor_acc_coef scaled it)
+    # 768 accumulation steps per score at D = 4096: wrong winners with exact relative gaps up to 8e-6 with the bound of
+    # D = 256; now the chain is cut into partial accumulators (segmented form), or the bound follows the chain
     ({}, ("150000", "4096", "1024", "1")),
-], ids=["multicast-cluster", "single-cta", "cta-pair", "cta-pair-bias-kstep", "cta-pair-streamed", "multicast-streamed",
-        "long-accumulation-chain"])
+], ids=["multicast-cluster", "single-cta", "cta-pair", "cta-pair-bias-kstep", "cta-pair-streamed-segmented",
+        "cta-pair-streamed-one-chain", "multicast-streamed", "long-accumulation-chain"])
 def test_tensor_kernel_variants_agree_with_simt(env, shape):
     """The forms of the tcgen05 candidate kernel (CTA pairs with cta_group::2 -- the default; sample tile in tensor
     memory for D <= 256, both operands streamed beyond; optionally wnorm as a bias k-step --, clusters with TMA

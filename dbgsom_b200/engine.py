@@ -170,8 +170,8 @@ class DeviceEngine:
 
     def close(self) -> None:
         self._ws.clear()
-        for name in ("X", "X16_hi", "X16_lo", "xnorm16", "W", "W32", "W16_hi", "W16_lo", "labels", "part", "hop",
-                     "_final_idx"):
+        for name in ("X", "X16_hi", "X16_lo", "xnorm16", "W", "W32", "W16_hi", "W16_lo", "Wb16", "_row_hash", "labels",
+                     "part", "hop", "_final_idx"):
             if hasattr(self, name):
                 setattr(self, name, None)
 

@@ -50,11 +50,26 @@ class BaseSom(BaseEstimator):
         Reproduce the reference's packed centre rows.  False gives
         the index-aligned batch update.
     bmu_backend : {"auto", "tensor", "simt"}, default "auto"
-        "tensor" = tcgen05 fp16 candidate search + exact re-score, "simt" = fp32 CUDA-core
-        candidate search + exact re-score.  Both return the same winners.
+        "tensor" = tcgen05 fp16 candidate search + exact float64 re-score of the candidates,
+        "simt" = fp32 CUDA-core candidate search (proven rounding bound) + the same re-score.
+        The tensor search keeps every prototype inside an error bound around the best approximate
+        score.  By default that bound is a CALIBRATED fraction of the Cauchy-Schwarz worst case
+        (rounding errors of 2D products do not align; csrc/common.cuh, tools/calibrate_bound.py), and a
+        sample with more candidates than the table holds is accepted without a full re-scan when
+        its best two approximate scores are provably inside the 1e-6 near-tie gate.  Winners
+        therefore equal the float64 reference outside that gate in every measured case, but only
+        `bound_scale=1.0, strict_ties=True` makes it a guarantee.
+    bound_scale : float, default 0.0
+        Coefficient of the tensor search's rounding bound relative to the worst case; 0 selects the
+        calibrated default, 1.0 the worst case (more samples re-scored, same winners).
+    strict_ties : bool, default False
+        Re-score samples whose candidate table overflowed against ALL prototypes in float64 instead of
+        accepting provable near-ties.  The post-training passes (`labels_`, hit counts, errors)
+        always run in this mode.
     distributed : bool, default False
         SPMD multi-GPU: every rank calls `fit` with its own shard of the samples; only the
-        per-neuron partial sums are all-reduced each epoch (`torch.distributed`, NCCL).
+        per-neuron partial sums are all-reduced each epoch (`torch.distributed`, NCCL).  The start
+        rows are drawn on rank 0 and broadcast, and `classes_` is the union over all shards.
     """
 
     def __init__(
@@ -81,6 +96,8 @@ class BaseSom(BaseEstimator):
         compat_pack_rows: bool = True,
         bmu_backend: str = "auto",
         distributed: bool = False,
+        bound_scale: float = 0.0,
+        strict_ties: bool = False,
     ) -> None:
         self.spreading_factor = spreading_factor
         self.n_iter = n_iter
@@ -104,6 +121,8 @@ class BaseSom(BaseEstimator):
         self.compat_pack_rows = compat_pack_rows
         self.bmu_backend = bmu_backend
         self.distributed = distributed
+        self.bound_scale = bound_scale
+        self.strict_ties = strict_ties
 
     # ------------------------------------------------------------------ hooks for subclasses
     def _check_input_data(self, X, y):
@@ -131,6 +150,8 @@ class BaseSom(BaseEstimator):
             device=self.device,
             bmu_backend=self.bmu_backend,
             distributed=self.distributed if distributed is None else distributed,
+            bound_scale=self.bound_scale,
+            strict_ties=self.strict_ties,
         )
 
     def _check_arguments(self) -> None:
@@ -151,11 +172,22 @@ class BaseSom(BaseEstimator):
         """Train the map on X (and y).  Same contract as dbgsom/BaseSom.py:88-131."""
         self._check_arguments()
         X, y = self._check_input_data(X, y)
-        if y is not None:
-            classes, y = np.unique(y, return_inverse=True)
-            self.classes_ = np.array(classes)
+        if y is None and self.growth_criterion == "entropy":
+            # the reference indexes `y[winners == j]` with y = None here (dbgsom/BaseSom.py:547-551) and dies with
+            # a TypeError in the first epoch; say what is wrong instead of silently growing on another criterion
+            raise ValueError("growth_criterion='entropy' needs class labels y (use SomClassifier)")
         self.random_state_ = check_random_state(self.random_state)
         engine = self._make_engine()
+        comm = getattr(engine, "comm", None)
+        self._comm = comm if comm is not None and getattr(comm, "enabled", False) and comm.world > 1 else None
+        if y is not None:
+            classes = np.unique(y)
+            if self._comm is not None:
+                # shards may hold different class sets: every rank must use the same index <-> class map (and the
+                # same histogram width in the collectives)
+                classes = self._comm.union_sorted(classes)
+            y = np.searchsorted(classes, y)
+            self.classes_ = np.array(classes)
         profile = os.environ.get("DBGSOM_PROFILE") == "1"  # wall time per stage + device time per kernel phase
         if profile and hasattr(engine, "enable_profiling"):
             engine.enable_profiling(True)
@@ -179,6 +211,7 @@ class BaseSom(BaseEstimator):
                     self.fit_profile_["device_ms"] = {k: round(float(np.sum(v)), 2) for k, v in engine.phase_times_ms().items()}
         finally:
             engine.close()
+            self._comm = None
         self.n_features_in_ = X.shape[1]
         self.n_iter_ = self._current_epoch
         return self
@@ -196,6 +229,9 @@ class BaseSom(BaseEstimator):
         # identical draw to `rng.choice(a=data, size=4, replace=False)` (row choice)
         rng = np.random.default_rng(seed=self.random_state)
         rows = rng.choice(stats["n_samples"], size=4, replace=False)
+        if self._comm is not None:
+            # an unseeded (or per-rank different) generator would give every rank its own four rows
+            rows = np.asarray(self._comm.broadcast_object(rows, src=0))
         self._topology = MapTopology.initial_square()
         engine.init_map_from_rows(rows, capacity=self._capacity_hint())
         self._hops_dirty = True

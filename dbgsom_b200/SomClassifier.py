@@ -40,9 +40,12 @@ class SomClassifier(BaseSom, TransformerMixin, ClassifierMixin):
             hit = row.sum()
             attrs = self.som_.nodes[node]
             prob = np.zeros(shape=self.classes_.shape)
-            if hit == 0:  # cannot happen after dead-neuron removal; kept for parity
+            if hit == 0:
+                # a survivor of the dead-neuron removal (hit_count > 0 on the PRE-update prototypes) that wins no
+                # sample on the updated map: the reference writes probabilities[-1] = 0 / hit_count, i.e. an
+                # all-zero row (dbgsom/SomClassifier.py:136-152)
                 attrs["label"] = -1
-                prob[-1] = 1
+                prob[-1] = 0.0 if attrs["hit_count"] > 0 else 1
             else:
                 best = np.flatnonzero(row == row.max())
                 attrs["label"] = int(best[np.argmin(first[j, best])])

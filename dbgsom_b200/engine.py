@@ -39,9 +39,10 @@ def _round_up(a: int, b: int) -> int:
 class Comm:
     """Thin wrapper over torch.distributed for the single collective of the path."""
 
-    def __init__(self, enabled: bool):
+    def __init__(self, enabled: bool, device=None):
         self.enabled = bool(enabled)
         self.rank, self.world = 0, 1
+        self.device = device  # CUDA device of this rank (object collectives stage through it under NCCL)
         if self.enabled:
             import torch.distributed as dist
 
@@ -60,6 +61,34 @@ class Comm:
         if self.enabled and self.world > 1:
             self.dist.broadcast(tensor, src=src)
         return tensor
+
+    def _on_device(self):
+        import contextlib
+
+        import torch
+
+        if self.device is not None and torch.device(self.device).type == "cuda":
+            return torch.cuda.device(self.device)
+        return contextlib.nullcontext()
+
+    def broadcast_object(self, obj, src: int = 0):
+        """The same Python object on every rank (rank `src`'s).  Used for decisions that must be identical
+        everywhere: the start rows drawn from an unseeded generator, for example."""
+        if not (self.enabled and self.world > 1):
+            return obj
+        box = [obj if self.rank == src else None]
+        with self._on_device():
+            self.dist.broadcast_object_list(box, src=src)
+        return box[0]
+
+    def union_sorted(self, values: np.ndarray) -> np.ndarray:
+        """Sorted union of the per-rank value sets (class labels of the shards), identical on every rank."""
+        if not (self.enabled and self.world > 1):
+            return np.asarray(values)
+        parts = [None] * self.world
+        with self._on_device():
+            self.dist.all_gather_object(parts, np.asarray(values))
+        return np.unique(np.concatenate([np.asarray(p_) for p_ in parts]))
 
     def exclusive_offset(self, n_local: int, device) -> tuple[int, int]:
         """(offset of this rank's shard, global sample count)."""
@@ -105,10 +134,11 @@ class DeviceEngine:
         self.bmu_backend = bmu_backend
         self.bound_scale = float(bound_scale)
         self.strict_ties = bool(strict_ties)
-        self.comm = Comm(distributed)
+        self.comm = Comm(distributed, self.dev)
         self.sample_offset = 0
         self.n_samples_global = 0
         self.launches = 0  # kernels + memsets enqueued by this engine (bench bookkeeping)
+        self.fp32_reruns = 0  # epochs repeated on the fp32 search because a prototype left the fp16 range
         self._prof = None
         self.last_bmu_stats = None
         self._ws = {}
@@ -464,16 +494,17 @@ class DeviceEngine:
             self._bias_ready = False
         return mpad
 
-    def _run_bmu(self, X, n: int, ldx: int, x16, W, m: int, n_bmu: int, want_dist: bool, idx, dist, backend=None):
+    def _run_bmu(self, X, n: int, ldx: int, x16, W, m: int, n_bmu: int, want_dist: bool, idx, dist, backend=None,
+                 strict=None):
         """prepare_w + candidate search + exact re-score for samples X against prototypes W."""
         be, n_pass = self._pick_backend(n, m) if backend is None else backend
         if W.shape[0] > self.W32.shape[0]:
             self.W32 = self.torch.zeros((W.shape[0], self.ldx), dtype=self.torch.float32, device=self.dev)
         with self._Phase(self, "prepare_w"):
             mpad = self._prepare_w(W, m, be == nat.BMU_TENSOR, n_pass == 3, top1=n_bmu == 1)
-        self._bmu_search(X, n, ldx, x16, W, m, mpad, n_bmu, want_dist, idx, dist, (be, n_pass))
+        self._bmu_search(X, n, ldx, x16, W, m, mpad, n_bmu, want_dist, idx, dist, (be, n_pass), strict=strict)
 
-    def _bmu_search(self, X, n, ldx, x16, W, m, mpad, n_bmu, want_dist, idx, dist, backend, ws_key="bmu"):
+    def _bmu_search(self, X, n, ldx, x16, W, m, mpad, n_bmu, want_dist, idx, dist, backend, ws_key="bmu", strict=None):
         """Candidate search + exact re-score of n sample rows (shadows of W must be current)."""
         be, n_pass = backend
         tensor = be == nat.BMU_TENSOR
@@ -495,7 +526,7 @@ class DeviceEngine:
         a.d_W, a.d_W32, a.d_wmax = W.data_ptr(), self.W32.data_ptr(), self.wmax.data_ptr()
         a.scale, a.M, a.Mpad, a.n_bmu = self.scale, m, mpad, n_bmu
         a.backend, a.n_pass, a.bound_scale, a.tie_rel = be, n_pass, self.bound_scale, 0.0
-        a.strict, a.want_dist = int(self.strict_ties), int(want_dist)
+        a.strict, a.want_dist = int(self.strict_ties if strict is None else strict), int(want_dist)
         a.d_idx, a.d_dist = idx.data_ptr(), (dist.data_ptr() if dist is not None else None)
         a.d_stats = self.bmu_stats.data_ptr()
         a.d_workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
@@ -635,18 +666,27 @@ class DeviceEngine:
             # a prototype left the fp16 range of the shadow (far outside the data hull): its
             # scores were clamped, so redo this epoch on the fp32 path from the same state
             self.cur ^= 1
+            self.fp32_reruns += 1
             return self.epoch(sigma, pack_rows, entropy_error, _force_simt=True)
         if use_hist:
             err = class_entropy(self.class_hist[:m].cpu().numpy())
         self.last_bmu_stats = None
         return {"error": err, "counts": counts, "change": change}
 
+    def last_winners_host(self) -> np.ndarray:
+        """BMU index of every local sample in the last `epoch` (int64 [N]; tests, diagnostics)."""
+        return self.idx.view(-1)[: self.N].cpu().numpy().astype(np.int64)
+
     def bmu_stats_host(self, reset: bool = True) -> dict:
         """Cumulative re-score statistics of all BMU searches since the last reset."""
         s = self.bmu_stats.cpu().numpy()
         if reset:
             self.bmu_stats.zero_()
-        return {"ambiguous": int(s[0]), "flagged": int(s[1]), "candidates": int(s[2]), "full_rescans": int(s[3])}
+        out = {"ambiguous": int(s[0]), "flagged": int(s[1]), "candidates": int(s[2]), "full_rescans": int(s[3]),
+               "fp32_reruns": int(self.fp32_reruns)}
+        if reset:
+            self.fp32_reruns = 0
+        return out
 
     def bmu_train(self, n_bmu: int, previous: bool = False):
         """BMUs of the training samples against the current (or pre-update) prototypes."""
@@ -679,7 +719,8 @@ class DeviceEngine:
             x16 = (self.X16_hi, self.X16_lo, self.xnorm16)
         idx = torch.empty((self.N, n_bmu), dtype=torch.int32, device=self.dev)
         dist = torch.empty((self.N, n_bmu), dtype=torch.float64, device=self.dev)
-        self._run_bmu(self.X, self.N, self.ldx, x16, W, m, n_bmu, True, idx, dist, backend=be)
+        # the post-training passes run once per fit: flagged samples are always re-scored against all prototypes
+        self._run_bmu(self.X, self.N, self.ldx, x16, W, m, n_bmu, True, idx, dist, backend=be, strict=True)
         return idx, dist, m
 
     def final_statistics(self, positions: np.ndarray, degrees: np.ndarray) -> dict:

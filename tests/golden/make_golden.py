@@ -13,6 +13,10 @@ Two kinds of fixture, both produced by importing the reference through oracle/_r
   seed (W, hop) are stored next to the outputs.
 * traj_*.npz  -- a full `fit` with per-epoch records (map size, per-neuron error, sigma,
   weight change, weight checksums) and every fitted attribute.
+* fitstep_*.npz -- states captured INSIDE a reference `fit` at chosen epochs (BASELINE.json configs[1]:
+  SomClassifier on the 70000 x 784 ten-class mixture): the prototypes, hop matrix and sigma the epoch body
+  saw (dbgsom/BaseSom.py:397-407) and what it produced (winners, E, updated prototypes), for
+  teacher-forced per-epoch parity at the config-2 shape; plus the fitted attributes of that fit.
 
 The fixtures depend on the installed numpy / scikit-learn / numba / networkx versions
 (recorded in each file).
@@ -134,6 +138,14 @@ TRAJ_CASES = [
                      learning_rate=0.1, max_neurons=25)),
 ]
 
+# BASELINE.json configs[1]: SomClassifier on the Fashion-MNIST-shaped 70000 x 784 mixture
+# with ten classes.  n_iter is kept small enough for CI (the reference needs ~0.5 s per epoch here); the states of
+# `capture` epochs are stored in full, everything else as per-epoch records like the traj_* files.
+FITSTEP_CASES = [
+    dict(name="c2_gmm784_clf", est="clf", data="gmm:70000:784:10:21:float32", cast="float32",
+         params=dict(random_state=7, n_iter=36, max_neurons=400), capture=[5, 11, 17, 18, 30]),
+]
+
 
 def recording(cls):
     class Rec(cls):
@@ -164,6 +176,27 @@ def recording(cls):
             self._log["avgdist_pre"] = self._extract_values_from_graph("average_distance").astype(np.float64)
             super()._delete_dead_neurons_from_graph(X)
 
+        def _get_winning_neurons(self, data, n_bmu):
+            dist, win = super()._get_winning_neurons(data, n_bmu)
+            cap = getattr(self, "_capture", None)
+            # the search of the epoch body (dbgsom/BaseSom.py:403): n_bmu == 1 on the full training matrix
+            if cap is not None and n_bmu == 1 and self._in_loop and self._current_epoch in cap["epochs"]:
+                e = self._current_epoch
+                cap[f"e{e}_W"] = self.weights_.copy()
+                cap[f"e{e}_hop"] = np.asarray(self._distance_matrix).copy()
+                cap[f"e{e}_sigma"] = np.float64(self._calculate_current_sigma())
+                cap[f"e{e}_winners"] = win.astype(np.int32)
+                cap[f"e{e}_dist"] = dist.copy()
+            return dist, win
+
+        def _grow_som(self, data, y):
+            self._in_loop = True
+            try:
+                super()._grow_som(data, y)
+            finally:
+                self._in_loop = False
+
+    Rec._in_loop = False
     Rec.__name__ = cls.__name__
     return Rec
 
@@ -229,8 +262,74 @@ def run_traj(case):
     )
 
 
+def run_fitstep(case):
+    """A reference fit at the config-2 shape with the epoch-body states of `capture` epochs stored."""
+    X, y = _datasets.load(case["data"])
+    X = np.ascontiguousarray(X.astype(case["cast"]))
+    base = SomVQ if case["est"] == "vq" else SomClassifier
+
+    class Cap(recording(base)):
+        def _update_weights(self, sample_weights, winners, data):
+            super()._update_weights(sample_weights, winners, data)
+            e = self._current_epoch
+            if e in self._capture["epochs"]:
+                self._capture[f"e{e}_W_new"] = self._extract_values_from_graph("weight")
+
+        def _write_accumulative_error(self, winners, y_, distances):
+            super()._write_accumulative_error(winners, y_, distances)
+            e = self._current_epoch
+            if e in self._capture["epochs"]:
+                self._capture[f"e{e}_E"] = self._extract_values_from_graph("error").astype(np.float64)
+
+    Cap.__name__ = base.__name__
+    som = Cap(**case["params"])
+    som._log = dict(M=[], sigma=[], change=[], wsum=[], wfro=[], n=[], E=[], phase=[])
+    som._capture = dict(epochs=set(case["capture"]))
+    som.fit(X) if case["est"] == "vq" else som.fit(X, y)
+    cap, log = som._capture, som._log
+    out = dict(
+        meta=json.dumps(case), versions=versions(), total_var=np.float64(som._total_variance),
+        growing_threshold=np.float64(som.growing_threshold_),
+        epoch_M=np.array(log["M"], dtype=np.int64), epoch_sigma=np.array(log["sigma"]),
+        epoch_change=np.array(log["change"]), epoch_wfro=np.array(log["wfro"]),
+        E_flat=np.concatenate(log["E"]), n_flat=np.concatenate(log["n"]),
+        neurons=np.array(som.neurons_, dtype=np.int64), nodes_pre=log["nodes_pre"],
+        weights=som.weights_.astype(np.float32),  # compared at 1e-4: float32 keeps the file small
+        n_iter_=np.int64(som.n_iter_), quantization_error=np.float64(som.quantization_error_),
+        topographic_error=np.float64(som.topographic_error_), converged=np.bool_(som.converged_),
+    )
+    if case["est"] != "vq":
+        out["classes"] = som.classes_
+        out["score"] = np.float64(som.score(X, y))
+        out["node_label"] = np.array([d["label"] for _, d in som.som_.nodes.data()], dtype=np.int64)
+    else:
+        out["labels"] = som.labels_.astype(np.int32)
+    for e in sorted(cap["epochs"]):
+        if f"e{e}_W" not in cap:
+            continue
+        hop = cap[f"e{e}_hop"]
+        h16 = np.full(hop.shape, 0xFFFF, dtype=np.uint16)
+        h16[np.isfinite(hop)] = hop[np.isfinite(hop)].astype(np.uint16)
+        m = cap[f"e{e}_W"].shape[0]
+        out[f"e{e}_W"] = cap[f"e{e}_W"]                              # float64: the exact state the reference saw
+        out[f"e{e}_hop"] = h16
+        out[f"e{e}_sigma"] = cap[f"e{e}_sigma"]
+        out[f"e{e}_winners"] = cap[f"e{e}_winners"].astype(np.uint8 if m <= 256 else np.uint16)
+        out[f"e{e}_dist_sum"] = np.float64(cap[f"e{e}_dist"].sum())  # (the per-neuron sums of dist are E)
+        out[f"e{e}_E"] = cap[f"e{e}_E"]
+        out[f"e{e}_W_new"] = cap[f"e{e}_W_new"].astype(np.float32)   # compared at 1e-5
+    out["captured"] = np.array(sorted(e for e in cap["epochs"] if f"e{e}_W" in cap), dtype=np.int64)
+    path = os.path.join(HERE, f"fitstep_{case['name']}.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, "epochs", len(log["M"]), "M per epoch", log["M"], "final", len(som.neurons_),
+          "QE", som.quantization_error_, "size", os.path.getsize(path))
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
+    for c in FITSTEP_CASES:
+        if not only or c["name"] in only:
+            run_fitstep(c)
     for c in STEP_CASES:
         if not only or c["name"] in only:
             run_step(c)

@@ -39,6 +39,20 @@ def _worker(rank, world, port, kind, out_dir):
 
         cls = SomVQ if kind == "vq" else SomClassifier
         Est = type(cls.__name__, (cls,), {"_make_engine": factory})
+        if kind == "clf_sorted_unseeded":
+            # shards with DIFFERENT class sets (samples sorted by label) and no seed: the start rows must come from
+            # one rank and classes_ from the union of the shards, or the ranks train different maps
+            order = np.argsort(y, kind="stable")
+            X, y = X[order], y[order]
+            est = Est(random_state=None, n_iter=12, distributed=True)
+            est.fit(X[lo:hi], y[lo:hi])
+            assert set(np.unique(y[lo:hi])) != set(np.unique(y)), "the shard should miss classes"
+            np.savez(
+                os.path.join(out_dir, f"rank{rank}.npz"), neurons=np.array(est.neurons_), weights=est.weights_,
+                classes=est.classes_, labels=est._extract_values_from_graph("label"),
+                prob=est._extract_values_from_graph("probabilities"), qe=est.quantization_error_,
+            )
+            return
         est = Est(random_state=0, n_iter=30, distributed=True)
         est.fit(X[lo:hi]) if kind == "vq" else est.fit(X[lo:hi], y[lo:hi])
         np.savez(
@@ -79,3 +93,21 @@ def test_two_ranks_equal_one_process(tmp_path, kind):
     if kind == "vq":
         n = X.shape[0]
         np.testing.assert_array_equal(np.concatenate([r0["local"], r1["local"]]), one.labels_)
+
+
+def test_two_ranks_unseeded_with_label_sorted_shards(tmp_path):
+    """with random_state=None every rank drew its own start rows, and classes_ came from the
+    local shard.  Both ranks must end with the same map, the union of the classes and a finite fit."""
+    import torch.multiprocessing as mp
+
+    import _datasets
+
+    mp.spawn(_worker, args=(2, _free_port(), "clf_sorted_unseeded", str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
+    for key in ("neurons", "weights", "classes", "labels", "prob", "qe"):
+        np.testing.assert_array_equal(r0[key], r1[key])
+    _, y = _datasets.load("digits")
+    np.testing.assert_array_equal(r0["classes"], np.unique(y))
+    assert r0["prob"].shape[1] == 10 and np.isfinite(r0["weights"]).all()
+    # the four start prototypes were real samples (a sum of unrelated rows would sit far outside the data)
+    assert r0["weights"].min() >= -1e-9 and r0["weights"].max() <= 16 + 1e-9

@@ -79,15 +79,27 @@ def test_final_statistics_match_numpy(shape):
     np.testing.assert_allclose(st["avg_dist"], avg, rtol=1e-12)
     bw = avg.mean()
     assert st["n_rows"] == m
-    if (gap >= 1e-6).all():
-        pos = topo.positions().astype(np.float64)
-        sep = pos[idx2[:, 0]] - pos[idx2[:, 1]]
-        # second BMUs may legitimately differ inside near-ties of the 2nd/3rd distance: compare loosely there
-        te = np.count_nonzero(np.sqrt((sep * sep).sum(axis=1)) > 1.5)
-        assert abs(st["te_count"] - te) <= max(2, 1e-4 * n)
-        np.testing.assert_array_equal(st["hits"], np.bincount(idx2[:, 0], minlength=m))
-        kern = np.exp(-(dist2[:, 0] ** 2) / (2 * bw**2)) / (bw * np.sqrt(2 * np.pi))
-        np.testing.assert_allclose(st["dens_sum"], np.bincount(idx2[:, 0], weights=kern, minlength=m), rtol=1e-9, atol=1e-300)
+    # Never skipped: samples whose two best float64 distances agree to 1e-6 (the parity gate's exempt set) may swap
+    # their first and second BMU on the device; every per-neuron statistic is bracketed by the two assignments of
+    # those samples and must be exact for all the others.
+    near = gap < 1e-6
+    assert near.mean() < 0.01
+    pos = topo.positions().astype(np.float64)
+    sep = pos[idx2[:, 0]] - pos[idx2[:, 1]]
+    # second BMUs may legitimately differ inside near-ties of the 2nd/3rd distance: compare loosely there
+    te = np.count_nonzero(np.sqrt((sep * sep).sum(axis=1)) > 1.5)
+    assert abs(st["te_count"] - te) <= max(2, 1e-4 * n) + near.sum()
+    first, second = idx2[:, 0], idx2[:, 1]
+    lo = np.bincount(first[~near], minlength=m)
+    hi = lo + np.bincount(first[near], minlength=m) + np.bincount(second[near], minlength=m)
+    assert (st["hits"] >= lo).all() and (st["hits"] <= hi).all() and st["hits"].sum() == n
+    kern = np.exp(-(dist2[:, 0] ** 2) / (2 * bw**2)) / (bw * np.sqrt(2 * np.pi))
+    dlo = np.bincount(first[~near], weights=kern[~near], minlength=m)
+    dhi = dlo + np.bincount(first[near], weights=kern[near], minlength=m) + np.bincount(second[near], weights=kern[near], minlength=m)
+    assert (st["dens_sum"] >= dlo * (1 - 1e-9) - 1e-300).all() and (st["dens_sum"] <= dhi * (1 + 1e-6) + 1e-300).all()
+    if not near.any():
+        np.testing.assert_array_equal(st["hits"], np.bincount(first, minlength=m))
+        np.testing.assert_allclose(st["dens_sum"], np.bincount(first, weights=kern, minlength=m), rtol=1e-9, atol=1e-300)
     assert st["qe_sum"] == pytest.approx(dist2[:, 0].sum(), rel=1e-9)
     np.testing.assert_allclose(st["weights"], W1)
     e.close()

@@ -96,3 +96,28 @@ def test_fit_reproduces_reference(path):
         np.testing.assert_array_equal(est.predict(X[:200]), g["predict_head"])
         np.testing.assert_allclose(est.predict_proba(X[:50]), g["proba_head"], rtol=1e-6, atol=1e-9)
         assert est.score(X, y) == pytest.approx(float(g["score"]))
+
+
+FITSTEP = golden_files("fitstep")
+
+
+@pytest.mark.parametrize("path", FITSTEP, ids=[os.path.basename(p)[8:-4] for p in FITSTEP])
+def test_config2_fit_reproduces_reference(path):
+    """BASELINE.json configs[1] (SomClassifier, 70000 x 784, ten classes, reduced n_iter): the host logic driven by
+    the oracle engine grows the reference's map epoch by epoch and ends with its neurons, prototypes and score."""
+    g = np.load(path, allow_pickle=False)
+    meta = json.loads(str(g["meta"]))
+    X, y = _datasets.load(meta["data"])
+    X = np.ascontiguousarray(X.astype(meta["cast"]))
+    est, eng = fit_with_oracle(SomClassifier, meta["params"], X, y)
+    np.testing.assert_array_equal(eng.log["M"], g["epoch_M"])
+    np.testing.assert_allclose(np.concatenate(eng.log["n"]), g["n_flat"])
+    np.testing.assert_allclose(np.concatenate(eng.log["E"]), g["E_flat"], rtol=1e-6, atol=1e-8)
+    np.testing.assert_array_equal(np.array(est.neurons_), g["neurons"])
+    scale = np.abs(g["weights"]).max()
+    assert np.abs(est.weights_ - g["weights"]).max() / scale < 1e-6
+    assert est.n_iter_ == int(g["n_iter_"])
+    assert est.quantization_error_ == pytest.approx(float(g["quantization_error"]), rel=1e-7)
+    assert est.topographic_error_ == pytest.approx(float(g["topographic_error"]), abs=1e-12)
+    np.testing.assert_array_equal(est._extract_values_from_graph("label"), g["node_label"])
+    np.testing.assert_array_equal(est.classes_, g["classes"])

@@ -92,3 +92,46 @@ def test_hop_matrix_grid_equals_floyd_warshall():
 
     g = nx.grid_2d_graph(4, 6)
     np.testing.assert_array_equal(O.hop_matrix_grid(4, 6), nx.floyd_warshall_numpy(g))
+
+
+# ------------------------------------------------------------------ BASELINE.json configs[1] (70000 x 784, ten classes)
+FITSTEP = golden_files("fitstep")
+
+
+def load_fitstep(path):
+    g = np.load(path, allow_pickle=False)
+    meta = json.loads(str(g["meta"]))
+    X, y = _datasets.load(meta["data"])
+    return g, meta, np.ascontiguousarray(X.astype(meta["cast"])), y
+
+
+def hop_float(h16):
+    hop = h16.astype(np.float64)
+    hop[h16 == 0xFFFF] = np.inf
+    return hop
+
+
+@pytest.mark.parametrize("path", FITSTEP, ids=[os.path.basename(p)[8:-4] for p in FITSTEP])
+def test_fitstep_states_match_reference(path):
+    """The oracle reproduces what the reference's epoch body computed INSIDE a config-2 fit, from the
+    prototypes / hop matrix / sigma that fit had at the captured epochs (float32 samples: the reference runs
+    sklearn's float32 -> float64 fallback path there)."""
+    g, meta, X, _ = load_fitstep(path)
+    assert len(g["captured"]) >= 4
+    for e in g["captured"]:
+        W, hop, sigma = g[f"e{e}_W"], hop_float(g[f"e{e}_hop"]), float(g[f"e{e}_sigma"])
+        assert W.shape[0] == int(g["epoch_M"][e]) and sigma == pytest.approx(float(g["epoch_sigma"][e]), rel=1e-15)
+        out = O.epoch_step(X, W, hop, sigma, float(g["total_var"]), pack=True)
+        gap = O.relative_gap(X, W)
+        safe = gap > 1e-9
+        np.testing.assert_array_equal(out["winners"][safe], g[f"e{e}_winners"].astype(np.int64)[safe])
+        assert safe.mean() > 0.999
+        if safe.all():
+            np.testing.assert_allclose(out["E"], g[f"e{e}_E"], rtol=2e-7, atol=1e-9)
+            scale = np.abs(g[f"e{e}_W_new"]).max()
+            assert np.abs(out["W_new"] - g[f"e{e}_W_new"]).max() / scale < 3e-7  # stored as float32
+        # dead neurons below live ones: the packed-row quirk is active in these states
+        n = out["n"]
+        live = np.flatnonzero(n > 0)
+        if e >= 11:
+            assert (n == 0).any() and live.max() > np.flatnonzero(n == 0).min()

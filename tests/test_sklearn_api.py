@@ -28,7 +28,7 @@ def test_hyperparameters_match_the_reference():
         params = cls().get_params()
         for k, v in REFERENCE_DEFAULTS.items():
             assert params[k] == v, k
-        assert set(params) - set(REFERENCE_DEFAULTS) == {"device", "compat_pack_rows", "bmu_backend", "distributed"}
+        assert set(params) - set(REFERENCE_DEFAULTS) == {"device", "compat_pack_rows", "bmu_backend", "distributed", "bound_scale", "strict_ties"}
 
 
 def test_clone_and_set_params_roundtrip():
@@ -99,3 +99,34 @@ def test_product_engine_is_the_default_and_needs_cuda():
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         SomVQ(n_iter=2).fit(np.random.default_rng(0).normal(size=(40, 3)))
     assert BaseSom._make_engine.__module__ == "dbgsom_b200.BaseSom"
+
+
+def test_entropy_growth_without_labels_is_an_error():
+    """SomVQ has no y: the reference dies in its first epoch (y[winners == j] with y = None); say why."""
+    X = np.random.default_rng(0).normal(size=(50, 5))
+    with pytest.raises(ValueError, match="entropy"):
+        with_oracle(SomVQ)(growth_criterion="entropy").fit(X)
+
+
+def test_survivor_without_samples_on_the_final_map_gets_zero_probabilities():
+    """dbgsom/SomClassifier.py:136-152: a neuron that survives dead-neuron removal (hit_count > 0 on the pre-update
+    prototypes) but wins nothing on the updated map gets label -1 and an ALL-ZERO probability row."""
+    import networkx as nx
+
+    class Hist:
+        def label_histogram(self, c):
+            counts = np.array([[3.0, 1.0, 0.0], [0.0, 0.0, 0.0]])
+            first = np.array([[0, 2, 9], [9, 9, 9]], dtype=np.int64)
+            return counts, first
+
+    est = SomClassifier()
+    est.classes_ = np.array([0, 1, 2])
+    est.neurons_ = [(0, 0), (0, 1)]
+    est.som_ = nx.Graph()
+    est.som_.add_node((0, 0), hit_count=4.0)
+    est.som_.add_node((0, 1), hit_count=2.0)
+    est._label_prototypes(None, Hist())
+    assert est.som_.nodes[(0, 0)]["label"] == 0
+    np.testing.assert_allclose(est.som_.nodes[(0, 0)]["probabilities"], [0.75, 0.25, 0.0])
+    assert est.som_.nodes[(0, 1)]["label"] == -1
+    np.testing.assert_array_equal(est.som_.nodes[(0, 1)]["probabilities"], [0.0, 0.0, 0.0])

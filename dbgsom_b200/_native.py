@@ -13,7 +13,8 @@ _LIB = None
 LIB_NAME = "libdbgsom_b200.so"
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
-ABI_VERSION = 6
+ABI_VERSION = 7
+SELECT_OFF, SELECT_FLAG, SELECT_REFINE = 0, 1, 2
 MAX_CAND = 8
 BMU_SIMT = 0
 BMU_TENSOR = 1
@@ -60,6 +61,11 @@ class BmuArgs(C.Structure):
         ("d_stats", c_void_p),
         ("d_workspace", c_void_p),
         ("workspace_bytes", c_size_t),
+        ("d_row_perm", c_void_p),
+        ("d_tile_mask", c_void_p),
+        ("reserved0", c_void_p),
+        ("select", c_int32),
+        ("select_granule", c_int32),
     ]
 
 
@@ -112,6 +118,12 @@ SIGNATURES = {
         c_int,
         [c_void_p, c_int64, c_int, c_int64, c_void_p, c_float, c_void_p, c_void_p, c_int64, c_void_p, c_void_p],
     ),
+    "dbgsom_prepare_x16_sorted": (
+        c_int,
+        [c_void_p, c_int64, c_int, c_int64, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p],
+    ),
+    "dbgsom_bmu_select_supported": (c_int, [c_int64, c_int64, c_int32, c_int32, c_int32]),
+    "dbgsom_accumulate_perm_offset": (c_size_t, [c_int64, c_int32]),
     "dbgsom_prepare_w": (
         c_int,
         [c_void_p, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p,

@@ -21,34 +21,55 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found; cannot build libdbgsom_b200.so")
 
 
-def needs_build() -> bool:
-    if not os.path.exists(LIB_PATH):
+OBJ_DIR = os.path.join(HERE, "build")
+
+
+def _stale(target: str, deps) -> bool:
+    if not os.path.exists(target):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + HEADERS
+    t = os.path.getmtime(target)
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def needs_build() -> bool:
+    return _stale(LIB_PATH, [os.path.join(CSRC, s) for s in SOURCES] + HEADERS)
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA source for sm_100a into one shared library; returns its path."""
+    """Compile every CUDA source for sm_100a (one object per source, in parallel, re-using objects that are newer
+    than their source and the headers) and link them into one shared library; returns its path."""
     if not force and not needs_build():
         return LIB_PATH
-    cmd = [
-        _nvcc(),
-        "-gencode", "arch=compute_100a,code=sm_100a",
-        "-lineinfo", "-O3", "-std=c++17",
-        "-shared", "-Xcompiler", "-fPIC",
-        "-o", LIB_PATH,
-    ] + [os.path.join(CSRC, s) for s in SOURCES]
+    from concurrent.futures import ThreadPoolExecutor
+
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
     if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd))
-    res = subprocess.run(cmd, capture_output=True, text=True)
+        flags.insert(0, "-Xptxas=-v")
+
+    def compile_one(src: str):
+        obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+        if not force and not _stale(obj, [os.path.join(CSRC, src)] + HEADERS):
+            return obj, None
+        cmd = [_nvcc(), *flags, "-c", os.path.join(CSRC, src), "-o", obj]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            return obj, res.stdout + res.stderr
+        if verbose:
+            print(res.stdout + res.stderr)
+        return obj, None
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    errors = [err for _, err in results if err]
+    if errors:
+        sys.stderr.write("\n".join(errors))
+        raise RuntimeError("nvcc failed building libdbgsom_b200.so")
+    link = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + [o for o, _ in results]
+    res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed building libdbgsom_b200.so")
-    if verbose:
-        print(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed linking libdbgsom_b200.so")
     return LIB_PATH
 
 

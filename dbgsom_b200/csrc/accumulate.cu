@@ -477,6 +477,10 @@ struct AccWorkspace {
 };
 
 size_t accumulate_workspace_bytes(int64_t N, int M) { return AccWorkspace::bytes(N, M); }
+size_t accumulate_perm_offset(int64_t N, int M) {
+  (void)N;
+  return 3 * round_up<size_t>((size_t)(M + 1) * 4, 256);
+}
 
 int run_accumulate(const dbgsom_accumulate_args& a, cudaStream_t s) {
   const AccWorkspace ws = AccWorkspace::carve(a.d_workspace, a.N, a.M);

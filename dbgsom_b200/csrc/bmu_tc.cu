@@ -56,6 +56,8 @@ constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int TC_THREADS = (EPI_WARP0 + EPI_WARPS) * 32;  // 640
 constexpr int KSUB = 4;       // candidate slots per (row, epilogue warp)
 constexpr int MAX_RES_KB = 4;  // resident A up to D = 256
+constexpr int kFlagMaxCols = 4096;                         // selective search: prototypes (padded) it covers
+constexpr int kFlagChunkBytes = kFlagMaxCols / 32 * BM * 4;  // FLAG pass: float minimum per (32-column chunk, row)
 
 // ------------------------------------------------------------------------------------------ PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -332,7 +334,7 @@ __device__ __noinline__ float2 slow_offer(float s, int col, uint32_t val_addr, u
 //      which leaves all shared memory to the prototype ring (5 stages instead of 2 at D = 256, 3 passes)
 //      and, for D <= 128, tensor-memory room for three accumulator buffers instead of two.
 // PAIRS: the streamed-operand form run as CTA pairs -- each CTA stages only its half of a prototype tile
-template <int NPASS, int BN, int RES_KB, int AKB, bool PAIRS = false>
+template <int NPASS, int BN, int RES_KB, int AKB, bool PAIRS = false, int EXTRA_BYTES = 0>
 struct Cfg {
   static constexpr bool ATM = AKB > 0;  // AKB: k-blocks of the sample tile held in tensor memory
   static constexpr bool XRES = RES_KB > 0;
@@ -341,7 +343,7 @@ struct Cfg {
   static constexpr int B_TILE_BYTES = BN * BK * 2;
   static_assert(!PAIRS || ASTREAM, "PAIRS is the streamed form");
   static constexpr int STAGE_BYTES = NA * (PAIRS ? B_TILE_BYTES / 2 : B_TILE_BYTES) + (ASTREAM ? NA * A_TILE_BYTES : 0);
-  static_assert(!ATM || (RES_KB == 0 && B_TILE_BYTES == A_TILE_BYTES), "TMEM-resident A shares the ring: BN must be 128");
+  static_assert(!ATM || (RES_KB == 0 && B_TILE_BYTES <= A_TILE_BYTES), "TMEM-resident A shares the ring: BN <= 128");
   static constexpr int A_COLS = AKB * NA * (BK / 2);                 // tensor-memory columns of the sample tile
   // accumulator buffers; the streamed pair form with 128-column tiles closes its accumulation chain every few
   // k-blocks (SEGM in the kernel) and rotates through four partial accumulators
@@ -354,9 +356,13 @@ struct Cfg {
   static constexpr int WN_SMEM_FLOATS = ATM ? 4096 : 0;  // wnorm staged in shared memory when it fits
   static constexpr int WN_BYTES = WN_SMEM_FLOATS * 4;
   static constexpr int SMEM_BUDGET = 227 * 1024 - 1024;  // minus alignment slack
-  static constexpr int STAGES_RAW = (SMEM_BUDGET - RES_BYTES - RING_BYTES - MISC_BYTES - WN_BYTES) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = RES_BYTES + STAGES * STAGE_BYTES + RING_BYTES + MISC_BYTES + WN_BYTES + 1024;
+  // (with the sample tile in tensor memory the ring is cut into 16 KB slots, see the kernel: budget in those units)
+  static constexpr int STAGE_UNIT = ATM ? (STAGE_BYTES > A_TILE_BYTES ? STAGE_BYTES : A_TILE_BYTES) : STAGE_BYTES;
+  // EXTRA_BYTES: the FLAG pass of the selective search keeps one minimum per (32-column chunk, row) of a row tile
+  static constexpr int STAGES_RAW = (SMEM_BUDGET - RES_BYTES - RING_BYTES - MISC_BYTES - WN_BYTES - EXTRA_BYTES) / STAGE_UNIT;
+  static constexpr int STAGES = STAGES_RAW > (ATM ? 12 : 8) ? (ATM ? 12 : 8) : STAGES_RAW;
+  static constexpr int RING_STAGE_BYTES = STAGES * STAGE_UNIT;  // bytes of the operand ring
+  static constexpr int SMEM_BYTES = RES_BYTES + RING_STAGE_BYTES + RING_BYTES + MISC_BYTES + WN_BYTES + EXTRA_BYTES + 1024;
   static constexpr int TMEM_COLS = ATM ? 512 : NACC * BN;  // accumulator buffers (+ the sample tile)
   static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
 };
@@ -375,7 +381,12 @@ struct Barriers {
 // shadow matrix per 128 sample rows: 7 TB/s at config 3, which is what kept the tensor pipe at 78 %)
 // drops by CL.  A ring stage is free again when the MMA warps of ALL CL CTAs have consumed it (their
 // commits arrive on every CTA's `empty` barrier).
-template <int NPASS, int NB, int BN, int RES_KB, int AKB, int CL, bool PAIR = false>
+// SEL: 0 = the classic search over all column tiles; 1 = FLAG pass of the selective search (one fp16 pass, lean
+// epilogue: per pair of row tiles, which column tiles hold a score inside the one-pass bound of one of its rows);
+// 2 = REFINE pass (the classic three-pass search over exactly those column tiles).  Both need the CTA-pair form with
+// the sample tile in tensor memory.  row_perm: the shadows are in sorted sample order (shadow row p = sample
+// row_perm[p]); every per-sample read and write below goes through it.
+template <int NPASS, int NB, int BN, int RES_KB, int AKB, int CL, bool PAIR = false, int SEL = 0>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     bmu_cand_tensor_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                            const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
@@ -385,8 +396,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                            const float* __restrict__ xnorm16,
                            const float* __restrict__ wmax, float bound_coef, float acc_coef,
                            int32_t* __restrict__ idx_out, int32_t* __restrict__ cand_idx,
-                           uint8_t* __restrict__ cand_count) {
-  using C = Cfg<NPASS, BN, RES_KB, AKB, PAIR && AKB == 0 && RES_KB == 0>;
+                           uint8_t* __restrict__ cand_count, const int32_t* __restrict__ row_perm,
+                           unsigned long long* __restrict__ tile_mask,
+                           int fg_shift, unsigned long long* __restrict__ sel_stats) {
+  using C = Cfg<NPASS, BN, RES_KB, AKB, PAIR && AKB == 0 && RES_KB == 0, SEL == 1 ? kFlagChunkBytes : 0>;
+  static_assert(SEL == 0 || (PAIR && AKB > 0 && NB == 1 && NPASS == (SEL == 1 ? 1 : 3)),
+                "selective search: CTA pairs, sample tile in tensor memory, one winner");
   constexpr bool ATM = C::ATM;
   static_assert(!PAIR || (CL == 2 && (ATM || C::ASTREAM)), "the CTA-pair form needs a cluster of two; sample tile in tensor memory or streamed");
   constexpr int B_PART_BYTES = PAIR ? C::B_TILE_BYTES / 2 : C::B_TILE_BYTES;  // prototype tile bytes per CTA and shadow
@@ -402,7 +417,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   static_assert(!SEGM || BN / 32 == EPI_SUBS, "segmented accumulation: one chunk per epilogue warp and tile");
   constexpr bool PAIR_ATM = PAIR && ATM;  // (the streamed pair form keeps whole stages: prototypes half + samples)
   constexpr int SLOT_BYTES = PAIR_ATM ? A_TILE_BYTES : C::STAGE_BYTES;
-  constexpr int NSLOT = PAIR_ATM ? (C::STAGES * C::STAGE_BYTES / A_TILE_BYTES > 16 ? 16 : C::STAGES * C::STAGE_BYTES / A_TILE_BYTES)
+  constexpr int NSLOT = PAIR_ATM ? (C::RING_STAGE_BYTES / A_TILE_BYTES > 16 ? 16 : C::RING_STAGE_BYTES / A_TILE_BYTES)
                                  : C::STAGES;
   static_assert(!PAIR_ATM || C::NA * B_PART_BYTES <= SLOT_BYTES, "a prototype k-block of the pair form must fit a slot");
   constexpr int NACC = C::NACC;
@@ -413,9 +428,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   uint8_t* res_a = smem;                               // [kb][hi|lo] A tiles (XRES)
   uint8_t* stages = smem + C::RES_BYTES;               // ring
   // wnorm staging, or -- in bias mode -- the constant A tile of the bias k-step (1024-byte aligned for its descriptor)
-  float* wn_smem = reinterpret_cast<float*>(stages + C::STAGES * C::STAGE_BYTES);
-  uint8_t* ring = stages + C::STAGES * C::STAGE_BYTES + C::WN_BYTES;  // candidate tables
+  float* wn_smem = reinterpret_cast<float*>(stages + C::RING_STAGE_BYTES);
+  uint8_t* ring = stages + C::RING_STAGE_BYTES + C::WN_BYTES;  // candidate tables
   Barriers* bars = reinterpret_cast<Barriers*>(ring + C::RING_BYTES);
+  float* chunk_min = reinterpret_cast<float*>(ring + C::RING_BYTES + C::MISC_BYTES);  // [chunk][row] (FLAG pass only)
   float* tab_val = reinterpret_cast<float*>(ring);
   int* tab_idx = reinterpret_cast<int*>(ring + BM * EPI_SUBS * KSUB * 4);  // = tab_val + kTabIdxOffset bytes
   float* row_min = reinterpret_cast<float*>(ring + BM * EPI_SUBS * KSUB * 8);
@@ -432,6 +448,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const int64_t n_iters = ceil_div<int64_t>(n_row_tiles, n_clusters * CL);
   constexpr uint16_t cl_mask = (uint16_t)((1u << CL) - 1u);
   auto tile_of = [&](int64_t it) { return (it * n_clusters + cluster_id) * CL + cl_rank; };
+  // selective search: masks and start tiles are kept per PAIR of row tiles (one cluster iteration)
+  const int64_t n_pairs = ceil_div<int64_t>(n_row_tiles, 2);
+  auto pair_of = [&](int64_t it) { return it * n_clusters + cluster_id; };
+  // column tiles of row-tile iteration `it`: all NT in order (classic, FLAG) or the set bits of the pair's mask (REFINE).  Every warp role derives the same sequence from global memory.
+  auto sel_mask = [&](int64_t it) -> unsigned long long {
+    const int64_t pr = pair_of(it);
+    return (SEL == 2 && pr < n_pairs) ? tile_mask[pr] : 0ull;
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_xh);
@@ -492,6 +516,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0, a_phase = 0;
+      unsigned long long sel_tiles = 0, sel_pairs = 0;
       for (int64_t it = 0; it < n_iters; ++it) {
         const int row0 = (int)(tile_of(it) * BM);
         if (XRES) {
@@ -530,7 +555,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             }
           }
         }
-        for (int nt = 0; nt < NT; ++nt) {
+        unsigned long long selm = sel_mask(it);
+        const int n_sel = SEL == 2 ? __popcll(selm) : NT;
+        if (SEL == 2 && cl_rank == 0 && pair_of(it) < n_pairs) {
+          sel_tiles += (unsigned)n_sel;
+          ++sel_pairs;
+        }
+        for (int ti = 0; ti < n_sel; ++ti) {
+          int nt = ti;
+          if (SEL == 2) {
+            nt = __ffsll((long long)selm) - 1;
+            selm &= selm - 1;
+          }
           for (int kb = 0; kb < KB; ++kb) {
             mbar_wait(&bars->empty[stage], phase ^ 1);
             uint8_t* st = stages + stage * SLOT_BYTES;
@@ -585,6 +621,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           }
         }
       }
+      if (SEL == 2 && sel_stats != nullptr && sel_pairs) {
+        atomicAdd(sel_stats + 0, sel_tiles);
+        atomicAdd(sel_stats + 1, sel_pairs);
+      }
     }
   } else if (warp == 1 && (!PAIR || cl_rank == 0)) {
     // ================================================================ MMA issuer (pair: the leader CTA only)
@@ -636,7 +676,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             }
           }
         }
-        for (int nt = 0; nt < NT; ++nt) {
+        const int n_sel = SEL == 2 ? __popcll(sel_mask(it)) : NT;
+        for (int nt = 0; nt < n_sel; ++nt) {
           uint32_t tmem_d = tmem_base + acc * BN;
           if (!SEGM) {
             mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
@@ -756,20 +797,112 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const float* wn_src = wn_in_smem ? wn_smem : wnorm;
     asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
     uint32_t acc = 0, acc_phase = 0;
+    if constexpr (SEL == 1) {
+      // ------------------------------------------------------------ FLAG pass: lean epilogue, no candidate tables
+      // Per 32-column chunk a thread (= sample row) forms its 32 one-pass scores and stores their minimum in shared
+      // memory, [chunk][row].  After the last column tile the row's smallest one-pass score is known, and with it the
+      // FINAL bound: every chunk whose minimum lies inside it sets the bit of its column tile.  (Testing against the
+      // running minimum instead flagged ~2x as many tiles: the bound is ~1e-3 of the score spread, so a running
+      // minimum that is not yet the final one lets whole neighbourhoods through.)  The bits of a row-tile pair are
+      // OR-ed over rows, warps and both CTAs into tile_mask.
+      uint32_t* cta_mask = reinterpret_cast<uint32_t*>(sub_state);  // two words, zero between row tiles
+      float* sub_min = reinterpret_cast<float*>(sub_state) + 4;      // [row][sub] minima of the four warps of a row
+      if (threadIdx.x == EPI_WARP0 * 32) cta_mask[0] = cta_mask[1] = 0u;
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
+      const int n_chunks = NT * CHUNKS;
+      for (int64_t it = 0; it < n_iters; ++it) {
+        const int64_t row = tile_of(it) * BM + t;
+        const bool valid = row < N;
+        const int64_t orow = valid ? (row_perm ? (int64_t)row_perm[row] : row) : 0;
+        const float tau = valid ? 2.f * tensor_score_bound(xnorm16[orow], wmax, bound_coef, acc_coef) : 0.f;
+        float m1 = kInf;
+        for (int nt = 0; nt < NT; ++nt) {
+          mbar_wait(&bars->tmem_full[acc], acc_phase);
+          tc_fence_after();
+          const uint32_t tmem_acc = tmem_base + lane_base + acc * BN;
+#pragma unroll 1
+          for (int c = (sub - nt * CHUNKS) & (EPI_SUBS - 1); c < CHUNKS; c += EPI_SUBS) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_acc + c * 32, r);
+            const int col = nt * BN + c * 32;
+            const float4* wn4 = reinterpret_cast<const float4*>(wn_src + col);
+            float4 w4[8];
+#pragma unroll
+            for (int g = 0; g < 8; ++g) w4[g] = wn4[g];
+            tmem_ld_wait();
+            float gmn[8];
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const float s0 = fmaf(-2.f, __uint_as_float(r[4 * g + 0]), w4[g].x);
+              const float s1 = fmaf(-2.f, __uint_as_float(r[4 * g + 1]), w4[g].y);
+              const float s2 = fmaf(-2.f, __uint_as_float(r[4 * g + 2]), w4[g].z);
+              const float s3 = fmaf(-2.f, __uint_as_float(r[4 * g + 3]), w4[g].w);
+              gmn[g] = fminf(fminf(s0, s1), fminf(s2, s3));
+            }
+            const float a1 = fminf(fminf(fminf(gmn[0], gmn[1]), fminf(gmn[2], gmn[3])),
+                                   fminf(fminf(gmn[4], gmn[5]), fminf(gmn[6], gmn[7])));
+            chunk_min[(nt * CHUNKS + c) * BM + t] = a1;
+            m1 = fminf(m1, a1);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->tmem_empty[acc]), 0));
+          if (++acc == NACC) {
+            acc = 0;
+            acc_phase ^= 1;
+          }
+        }
+        sub_min[t * EPI_SUBS + sub] = m1;
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
+        const float4 sm4 = *reinterpret_cast<const float4*>(sub_min + t * EPI_SUBS);
+        const float thr = fminf(fminf(sm4.x, sm4.y), fminf(sm4.z, sm4.w)) + tau;
+        uint32_t mlo = 0u, mhi = 0u;
+        if (valid) {
+          for (int ch = sub; ch < n_chunks; ch += EPI_SUBS) {
+            const uint32_t bit = (uint32_t)(ch * 32) >> fg_shift;
+            const uint32_t inb = chunk_min[ch * BM + t] <= thr ? 1u : 0u;
+            mlo |= bit < 32u ? inb << bit : 0u;
+            mhi |= bit >= 32u ? inb << (bit - 32u) : 0u;
+          }
+        }
+        mlo = __reduce_or_sync(kFullMask, mlo);
+        mhi = __reduce_or_sync(kFullMask, mhi);
+        if (lane == 0) {
+          if (mlo) atomicOr(&cta_mask[0], mlo);
+          if (mhi) atomicOr(&cta_mask[1], mhi);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
+        if (threadIdx.x == EPI_WARP0 * 32) {
+          const unsigned long long m64 = (unsigned long long)cta_mask[0] | ((unsigned long long)cta_mask[1] << 32);
+          const int64_t pr = pair_of(it);
+          if (m64 && pr < n_pairs) atomicOr(tile_mask + pr, m64);
+          cta_mask[0] = cta_mask[1] = 0u;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
+      }
+    } else
     for (int64_t it = 0; it < n_iters; ++it) {
       const int64_t row = tile_of(it) * BM + t;
-      const float tau = row < N ? 2.f * tensor_score_bound(xnorm16[row], wmax, bound_coef, acc_coef) : 0.f;
+      const int64_t orow = row < N ? (row_perm ? (int64_t)row_perm[row] : row) : 0;
+      const float tau = row < N ? 2.f * tensor_score_bound(xnorm16[orow], wmax, bound_coef, acc_coef) : 0.f;
       float m1 = kInf, m2 = kInf, thr = kInf, evicted = __int_as_float(0x7f800000);
       float gate = __int_as_float(0x7f800000);  // fast gate of my table (see slow_offer); +inf while a slot is free
       asm volatile("st.shared.v4.f32 [%0], {%1,%1,%1,%1};" ::"r"(my_val_addr), "f"(gate) : "memory");
       asm volatile("st.shared.v4.s32 [%0], {%1,%1,%1,%1};" ::"r"(my_idx_addr), "r"(0x7fffffff) : "memory");
-      for (int nt = 0; nt < NT; ++nt) {
+      unsigned long long selm = sel_mask(it);
+      const int n_sel = SEL == 2 ? __popcll(selm) : NT;
+      for (int ti = 0; ti < n_sel; ++ti) {
+        int nt = ti;
+        if (SEL == 2) {
+          nt = __ffsll((long long)selm) - 1;
+          selm &= selm - 1;
+        }
         mbar_wait(&bars->tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t tmem_acc = tmem_base + lane_base + acc * BN;
         // every fourth chunk (counted over the whole row tile) is mine: start at it instead of testing each one
 #pragma unroll 1
-        for (int c = (sub - nt * CHUNKS) & (EPI_SUBS - 1); c < CHUNKS; c += EPI_SUBS) {
+        for (int c = (sub - ti * CHUNKS) & (EPI_SUBS - 1); c < CHUNKS; c += EPI_SUBS) {
           uint32_t r[32];
           if (SEGM) {
             // my chunk of every partial accumulator of this tile, summed in fp32 registers; a partial buffer goes back
@@ -958,12 +1091,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         if (row < N) {
           const int valid = overflow ? 0 : cnt;
 #pragma unroll
-          for (int q = 0; q < kMaxCand; ++q) cand_idx[row * kMaxCand + q] = q < valid ? out[q] : -1;
+          for (int q = 0; q < kMaxCand; ++q) cand_idx[orow * kMaxCand + q] = q < valid ? out[q] : -1;
           // a flagged row has no candidate list; its first slot carries the gap between the two smallest
           // approximate scores instead (>= 0, float bits), which tightens the near-tie test of the re-score
-          if (overflow) cand_idx[row * kMaxCand] = __float_as_int(fmaxf(sv - bv, 0.f));
-          cand_count[row] = (uint8_t)(overflow ? DBGSOM_CAND_OVERFLOW : cnt);
-          idx_out[row * NB] = best;
+          if (overflow) cand_idx[orow * kMaxCand] = __float_as_int(fmaxf(sv - bv, 0.f));
+          cand_count[orow] = (uint8_t)(overflow ? DBGSOM_CAND_OVERFLOW : cnt);
+          idx_out[orow * NB] = best;
         }
         row_min[t] = kInf;
       }
@@ -1029,9 +1162,9 @@ int sm_count() {
   return n;
 }
 
-template <int NPASS, int NB, int BN, int RES_KB, int AKB, int CL, bool PAIR = false>
+template <int NPASS, int NB, int BN, int RES_KB, int AKB, int CL, bool PAIR = false, int SEL = 0>
 int launch_cfg_cl(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t s) {
-  using C = Cfg<NPASS, BN, RES_KB, AKB, PAIR && AKB == 0 && RES_KB == 0>;
+  using C = Cfg<NPASS, BN, RES_KB, AKB, PAIR && AKB == 0 && RES_KB == 0, SEL == 1 ? kFlagChunkBytes : 0>;
   CUtensorMap mxh, mxl, mwh, mwl;
   int rc = make_map(&mxh, a.d_X16_hi, a.N, a.ld16, BM);
   if (rc) return rc;
@@ -1047,7 +1180,7 @@ int launch_cfg_cl(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t
     mwl = mwh;
   }
   CUtensorMap mwb = mwh;
-  const bool with_bias = PAIR && C::ATM && a.d_Wb16 != nullptr && a.d_bias_scale != nullptr;
+  const bool with_bias = SEL == 0 && PAIR && C::ATM && a.d_Wb16 != nullptr && a.d_bias_scale != nullptr;
   if (with_bias) {
     rc = make_map(&mwb, a.d_Wb16, a.Mpad, BK, BN / CL);
     if (rc) return rc;
@@ -1061,7 +1194,7 @@ int launch_cfg_cl(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t
       fprintf(stderr, "dbgsom: K1 takes wnorm through the bias k-step, E = %g\n", e);
     }
   }
-  auto kern = bmu_cand_tensor_kernel<NPASS, NB, BN, RES_KB, AKB, CL, PAIR>;
+  auto kern = bmu_cand_tensor_kernel<NPASS, NB, BN, RES_KB, AKB, CL, PAIR, SEL>;
   DBGSOM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   const int KB = (int)(a.ld16 / BK);
   const int NT = a.Mpad / BN;  // prototypes are permuted over all Mpad shadow rows
@@ -1098,7 +1231,10 @@ int launch_cfg_cl(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t
   const int pstride = a.proto_stride > 0 && a.Mpad <= 65535 && a.proto_stride < a.Mpad ? a.proto_stride : 0;
   DBGSOM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, mxh, mxl, mwh, mwl, mwb, with_bias ? a.d_bias_scale : (const float*)nullptr,
                                      a.N, KB, NT, a.d_wnorm, a.d_proto_of_col, pstride,
-                                     a.n_bmu == 1 ? a.ties_any : 0, a.d_xnorm16, a.d_wmax, coef, acc_coef, a.d_idx, ws.cand_idx, ws.cand_count));
+                                     a.n_bmu == 1 ? a.ties_any : 0, a.d_xnorm16, a.d_wmax, coef, acc_coef, a.d_idx, ws.cand_idx, ws.cand_count,
+                                     a.d_row_perm, reinterpret_cast<unsigned long long*>(a.d_tile_mask),
+                                     a.select_granule == 64 ? 6 : 7,
+                                     a.d_stats ? reinterpret_cast<unsigned long long*>(a.d_stats) + 4 : (unsigned long long*)nullptr));
   DBGSOM_LAUNCH_CHECK();
   return DBGSOM_OK;
 }
@@ -1183,8 +1319,39 @@ float tensor_acc_coef_args(const dbgsom_bmu_args& a) {
   return tensor_acc_coef(a.n_pass, a.ld16, a.strict);
 }
 
+bool bmu_select_supported(int64_t N, int64_t ld16, int Mpad, int n_bmu, int granule) {
+  if (n_bmu != 1 || (granule != 64 && granule != 128)) return false;
+  if (ld16 % BK != 0 || ld16 / BK > MAX_RES_KB || ld16 / BK < 1) return false;  // sample tile in tensor memory: D <= 256
+  if (Mpad % 256 != 0 || Mpad / granule > 64 || Mpad > kFlagMaxCols) return false;  // one mask bit per column tile
+  if (ceil_div<int64_t>(N, BM) < sm_count()) return false;                        // CTA pairs need a full wave of row tiles
+  return cluster_size() >= 2;
+}
+
+namespace {
+template <int SEL>
+int launch_select(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t s) {
+  const int KB = (int)(a.ld16 / BK);
+  if constexpr (SEL == 1) {  // FLAG: one pass, 128-column MMAs
+    if (KB <= 2) return launch_cfg_cl<1, 1, 128, 0, 2, 2, true, 1>(a, ws, s);
+    return launch_cfg_cl<1, 1, 128, 0, 4, 2, true, 1>(a, ws, s);
+  } else {                   // REFINE: three passes over the flagged column tiles of `select_granule` prototypes
+    if (a.select_granule == 64) {
+      if (KB <= 2) return launch_cfg_cl<3, 1, 64, 0, 2, 2, true, 2>(a, ws, s);
+      return launch_cfg_cl<3, 1, 64, 0, 4, 2, true, 2>(a, ws, s);
+    }
+    if (KB <= 2) return launch_cfg_cl<3, 1, 128, 0, 2, 2, true, 2>(a, ws, s);
+    return launch_cfg_cl<3, 1, 128, 0, 4, 2, true, 2>(a, ws, s);
+  }
+}
+}  // namespace
+
 int launch_bmu_cand_tensor(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t s) {
   if (a.ld16 % BK != 0 || a.Mpad % 256 != 0 || a.Mpad < a.M) return DBGSOM_E_UNSUPPORTED;
+  if (a.select != DBGSOM_SELECT_OFF) {
+    if (!bmu_select_supported(a.N, a.ld16, a.Mpad, a.n_bmu, a.select_granule) || !a.d_proto_of_col) return DBGSOM_E_UNSUPPORTED;
+    if (a.N > 0x7fffff00LL) return DBGSOM_E_UNSUPPORTED;
+    return a.select == DBGSOM_SELECT_FLAG ? launch_select<1>(a, ws, s) : launch_select<2>(a, ws, s);
+  }
   if (!a.d_proto_of_col) return DBGSOM_E_BADARG;
   if ((reinterpret_cast<uintptr_t>(a.d_X16_hi) & 15u) || (reinterpret_cast<uintptr_t>(a.d_W16_hi) & 15u) ||
       (reinterpret_cast<uintptr_t>(a.d_wnorm) & 15u))

@@ -3,8 +3,10 @@
 
 namespace dbgsom {
 int run_colstats(const float*, int64_t, int, int64_t, const float*, double*, cudaStream_t);
-int run_prepare_x16(const float*, int64_t, int, int64_t, const float*, float, uint16_t*, uint16_t*, int64_t, float*,
-                    cudaStream_t);
+int run_prepare_x16(const float*, int64_t, int, int64_t, const float*, float, const int32_t*, uint16_t*, uint16_t*, int64_t,
+                    float*, cudaStream_t);
+size_t accumulate_perm_offset(int64_t, int);
+bool bmu_select_supported(int64_t N, int64_t ld16, int Mpad, int n_bmu, int granule);
 int run_prepare_w(const double*, int, int, const float*, float, float*, uint16_t*, uint16_t*, int64_t, int,
                   const int32_t*, float*, double*, float*, cudaStream_t);
 int run_exclude_duplicates(const double*, int, int, const int32_t*, float*, unsigned long long*, cudaStream_t);
@@ -63,7 +65,19 @@ int dbgsom_prepare_x16(const float* d_X, int64_t N, int D, int64_t ldx, const fl
                        uint16_t* d_X16_hi, uint16_t* d_X16_lo, int64_t ld16, float* d_xnorm16, void* stream) {
   if (!d_X || !d_shift || !d_X16_hi || !d_xnorm16 || N <= 0 || D <= 0 || ldx < D || ld16 < D) return DBGSOM_E_BADARG;
   if (ld16 % 64 != 0) return DBGSOM_E_UNSUPPORTED;
-  return run_prepare_x16(d_X, N, D, ldx, d_shift, scale, d_X16_hi, d_X16_lo, ld16, d_xnorm16, as_stream(stream));
+  return run_prepare_x16(d_X, N, D, ldx, d_shift, scale, nullptr, d_X16_hi, d_X16_lo, ld16, d_xnorm16, as_stream(stream));
+}
+
+int dbgsom_prepare_x16_sorted(const float* d_X, int64_t N, int D, int64_t ldx, const float* d_shift, float scale,
+                              const int32_t* d_perm, uint16_t* d_X16_hi, uint16_t* d_X16_lo, int64_t ld16,
+                              float* d_xnorm16, void* stream) {
+  if (!d_X || !d_shift || !d_perm || !d_X16_hi || !d_xnorm16 || N <= 0 || D <= 0 || ldx < D || ld16 < D) return DBGSOM_E_BADARG;
+  if (ld16 % 64 != 0 || N > 0x7fffffffLL) return DBGSOM_E_UNSUPPORTED;
+  return run_prepare_x16(d_X, N, D, ldx, d_shift, scale, d_perm, d_X16_hi, d_X16_lo, ld16, d_xnorm16, as_stream(stream));
+}
+
+int dbgsom_bmu_select_supported(int64_t N, int64_t ld16, int32_t Mpad, int32_t n_bmu, int32_t select_granule) {
+  return bmu_select_supported(N, ld16, Mpad, n_bmu, select_granule) ? 1 : 0;
 }
 
 int dbgsom_prepare_w(const double* d_W, int M, int D, const float* d_shift, float scale, float* d_W32,
@@ -91,6 +105,13 @@ static int check_bmu_args(const dbgsom_bmu_args* a) {
     if (!a->d_X16_hi || !a->d_W16_hi || !a->d_wnorm || !a->d_xnorm16 || !a->d_proto_of_col) return DBGSOM_E_BADARG;
     if (a->n_pass != 1 && a->n_pass != 3) return DBGSOM_E_BADARG;
     if (a->n_pass == 3 && (!a->d_X16_lo || !a->d_W16_lo)) return DBGSOM_E_BADARG;
+    if (a->select != DBGSOM_SELECT_OFF) {
+      if (a->select != DBGSOM_SELECT_FLAG && a->select != DBGSOM_SELECT_REFINE) return DBGSOM_E_BADARG;
+      if (!a->d_tile_mask || a->n_pass != (a->select == DBGSOM_SELECT_FLAG ? 1 : 3)) return DBGSOM_E_BADARG;
+      if (!bmu_select_supported(a->N, a->ld16, a->Mpad, a->n_bmu, a->select_granule)) return DBGSOM_E_UNSUPPORTED;
+    }
+  } else if (a->select != DBGSOM_SELECT_OFF || a->d_row_perm) {
+    return DBGSOM_E_BADARG;
   }
   if (a->D % 4 != 0 || a->ldx % 4 != 0 || !aligned16(a->d_X) || !aligned16(a->d_W32) || !aligned16(a->d_W))
     return DBGSOM_E_UNSUPPORTED;
@@ -132,6 +153,7 @@ int dbgsom_bmu(const dbgsom_bmu_args* a, void* stream) {
 }
 
 size_t dbgsom_accumulate_workspace_bytes(int64_t N, int32_t M) { return accumulate_workspace_bytes(N, M); }
+size_t dbgsom_accumulate_perm_offset(int64_t N, int32_t M) { return accumulate_perm_offset(N, M); }
 
 int dbgsom_accumulate(const dbgsom_accumulate_args* a, void* stream) {
   if (!a || !a->d_X || !a->d_bmu || !a->d_W || !a->d_part || !a->d_workspace) return DBGSOM_E_BADARG;

@@ -50,19 +50,22 @@ __global__ void __launch_bounds__(CS_COLS * CS_ROWS) colstats_kernel(const float
 
 // ------------------------------------------------------------------------------------------ shadows
 // x' = (X[i, :] - shift) * scale;  X16_hi = half(x'), X16_lo = half(x' - X16_hi) (optional), zero
-// padded to ld16;  xnorm16[i] = ||x'||_2 rounded up.
+// padded to ld16;  xnorm16[i] = ||x'||_2 rounded up.  With `perm`, shadow row p is built from sample perm[p]
+// (sorted sample order of the selective search); xnorm16 stays indexed by sample.
 __global__ void __launch_bounds__(256) prepare_x16_kernel(const float* __restrict__ X, int64_t N, int D, int64_t ldx,
                                                          const float* __restrict__ shift, float scale,
+                                                         const int32_t* __restrict__ perm,
                                                          __half* __restrict__ X16_hi, __half* __restrict__ X16_lo,
                                                          int64_t ld16, float* __restrict__ xnorm16) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= N) return;
+  const int64_t src = perm ? (int64_t)perm[row] : row;
   float acc = 0.f;
   for (int64_t d = lane * 2; d < ld16; d += 64) {
     float v0 = 0.f, v1 = 0.f;
-    if (d < D) v0 = (X[row * ldx + d] - shift[d]) * scale;
-    if (d + 1 < D) v1 = (X[row * ldx + d + 1] - shift[d + 1]) * scale;
+    if (d < D) v0 = (X[src * ldx + d] - shift[d]) * scale;
+    if (d + 1 < D) v1 = (X[src * ldx + d + 1] - shift[d + 1]) * scale;
     v0 = fminf(fmaxf(v0, -65504.f), 65504.f);  // the host picks `scale` so that this never binds
     v1 = fminf(fmaxf(v1, -65504.f), 65504.f);
     const __half2 h = __floats2half2_rn(v0, v1);
@@ -75,7 +78,7 @@ __global__ void __launch_bounds__(256) prepare_x16_kernel(const float* __restric
     acc = fmaf(v1, v1, acc);
   }
   acc = warp_sum(acc);
-  if (lane == 0) xnorm16[row] = sqrtf(acc) * (1.f + 1e-6f);
+  if (lane == 0) xnorm16[src] = sqrtf(acc) * (1.f + 1e-6f);
 }
 
 // column means of W (float64): wshift[d] = mean_j W[j, d]
@@ -306,10 +309,10 @@ int run_colstats(const float* X, int64_t N, int D, int64_t ldx, const float* shi
   return DBGSOM_OK;
 }
 
-int run_prepare_x16(const float* X, int64_t N, int D, int64_t ldx, const float* shift, float scale, uint16_t* X16_hi,
-                    uint16_t* X16_lo, int64_t ld16, float* xnorm16, cudaStream_t s) {
+int run_prepare_x16(const float* X, int64_t N, int D, int64_t ldx, const float* shift, float scale, const int32_t* perm,
+                    uint16_t* X16_hi, uint16_t* X16_lo, int64_t ld16, float* xnorm16, cudaStream_t s) {
   prepare_x16_kernel<<<(unsigned)ceil_div<int64_t>(N, 8), 256, 0, s>>>(
-      X, N, D, ldx, shift, scale, reinterpret_cast<__half*>(X16_hi), reinterpret_cast<__half*>(X16_lo), ld16, xnorm16);
+      X, N, D, ldx, shift, scale, perm, reinterpret_cast<__half*>(X16_hi), reinterpret_cast<__half*>(X16_lo), ld16, xnorm16);
   DBGSOM_LAUNCH_CHECK();
   return DBGSOM_OK;
 }

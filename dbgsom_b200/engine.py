@@ -36,6 +36,20 @@ def _round_up(a: int, b: int) -> int:
     return (a + b - 1) // b * b
 
 
+def map_patch_order(positions: np.ndarray) -> np.ndarray:
+    """Prototype indices in Z-order (Morton code) of their grid positions: consecutive runs of 32 / 64 / 128
+    prototypes are compact patches of the map (4 x 8, 8 x 8, 8 x 16 cells on a full grid).  The selective BMU search
+    lays the shadow columns out in this order, so the prototypes that compete for one sample -- neighbours on the
+    map -- share few column tiles."""
+    pos = np.asarray(positions, dtype=np.int64).reshape(-1, 2)
+    p = pos - pos.min(axis=0)
+    code = np.zeros(len(p), dtype=np.int64)
+    for b in range(int(max(1, int(p.max()).bit_length()))):
+        code |= ((p[:, 0] >> b) & 1) << (2 * b + 1)
+        code |= ((p[:, 1] >> b) & 1) << (2 * b)
+    return np.argsort(code, kind="stable").astype(np.int32)
+
+
 class Comm:
     """Thin wrapper over torch.distributed for the single collective of the path."""
 
@@ -134,6 +148,18 @@ class DeviceEngine:
         self.bmu_backend = bmu_backend
         self.bound_scale = float(bound_scale)
         self.strict_ties = bool(strict_ties)
+        # Selective search (csrc/bmu_tc.cu, SEL): one fp16 pass over everything, split-fp16 passes only over the
+        # column tiles it cannot rule out.  Needs the samples sorted by winner (rebuilt every `resort_every` epochs
+        # from the permutation K2 leaves behind) and the shadow columns in map-patch order.  DBGSOM_SELECT=0 turns it off.
+        self.select_enabled = os.environ.get("DBGSOM_SELECT", "1") != "0"
+        self.select_granule = int(os.environ.get("DBGSOM_SELECT_GRANULE", "64"))
+        self.resort_every = int(os.environ.get("DBGSOM_RESORT_EVERY", "8"))
+        self.row_perm = None      # int32 [N]: shadow row p holds sample row_perm[p] (None = natural order)
+        self.tile_mask = None
+        self._sort_age = 0
+        self._map_order = None    # prototype indices in map-patch order (from the topology)
+        self._perm_cache = {}
+        self._epoch_kinds = {"selective": 0, "classic": 0}
         self.comm = Comm(distributed, self.dev)
         self.sample_offset = 0
         self.n_samples_global = 0
@@ -200,8 +226,9 @@ class DeviceEngine:
 
     def close(self) -> None:
         self._ws.clear()
+        self._perm_cache.clear()
         for name in ("X", "X16_hi", "X16_lo", "xnorm16", "W", "W32", "W16_hi", "W16_lo", "Wb16", "_row_hash", "labels",
-                     "part", "hop", "_final_idx"):
+                     "part", "hop", "_final_idx", "row_perm", "tile_mask"):
             if hasattr(self, name):
                 setattr(self, name, None)
 
@@ -266,6 +293,7 @@ class DeviceEngine:
         torch = self.torch
         if self.X16_hi is not None and (self.X16_lo is not None or not need_lo):
             return
+        self.row_perm = None  # (re)built in natural sample order
         self.X16_hi = torch.empty((self.N, self.ld16), dtype=torch.float16, device=self.dev)
         self.X16_lo = torch.empty((self.N, self.ld16), dtype=torch.float16, device=self.dev) if need_lo else None
         self.xnorm16 = torch.empty(self.N, dtype=torch.float32, device=self.dev)
@@ -294,7 +322,7 @@ class DeviceEngine:
         self.part = torch.zeros(cap * self.ldx + 3 * cap, dtype=torch.float64, device=self.dev)
         self.change = torch.zeros(1, dtype=torch.float64, device=self.dev)
         self.idx = torch.empty((self.N, 2), dtype=torch.int32, device=self.dev)
-        self.bmu_stats = torch.zeros(4, dtype=torch.int64, device=self.dev)
+        self.bmu_stats = torch.zeros(8, dtype=torch.int64, device=self.dev)
         self.class_hist = (
             torch.zeros((cap, self.n_classes), dtype=torch.int32, device=self.dev) if self.labels is not None else None
         )
@@ -350,9 +378,10 @@ class DeviceEngine:
             self.M = m
             self.n_previous_rows = m
 
-    def set_hops(self, hop_u16: np.ndarray) -> None:
+    def set_hops(self, hop_u16: np.ndarray, positions: np.ndarray | None = None) -> None:
         torch = self.torch
         m = hop_u16.shape[0]
+        self._map_order = map_patch_order(positions) if positions is not None else None
         finite = hop_u16[hop_u16 != 0xFFFF]
         self.hop_max = int(finite.max()) if finite.size else 0
         # uint16 travels as int16 bit patterns (torch has no uint16 arithmetic; none is needed)
@@ -367,8 +396,9 @@ class DeviceEngine:
         torch = self.torch
         m = len(topo)
         if m > nat.HOPS_MAX_M:
-            self.set_hops(topo.hop_matrix_u16())
+            self.set_hops(topo.hop_matrix_u16(), topo.positions())
             return
+        self._map_order = map_patch_order(topo.positions())
         with torch.cuda.device(self.dev):
             d_adj = torch.from_numpy(topo.adjacency_table()).to(self.dev)
             self.hop = torch.empty((m, m), dtype=torch.int16, device=self.dev)
@@ -424,27 +454,45 @@ class DeviceEngine:
         big = m >= 128 and n * m * self.ldx >= (1 << 31)
         return (nat.BMU_TENSOR, 3) if big else (nat.BMU_SIMT, 0)
 
-    def _prepare_w(self, W, m: int, tensor: bool, need_lo: bool, top1: bool = True) -> int:
+    def _column_order(self, m: int, mpad: int, map_order: bool):
+        """(proto_of_col, col_of_proto, stride) device tables of the shadow-column permutation.
+
+        Classic search: a fixed scattered visiting order (shadow row c holds prototype (c * stride) % mpad, stride ~
+        mpad / golden ratio and coprime to mpad) -- a low-discrepancy sequence over the map that the kernel can
+        evaluate in registers, so running minima are rarely improved.  Selective search: map-patch order
+        (`map_patch_order`), padding columns last."""
+        torch = self.torch
+        key = (mpad, "map", id(self._map_order)) if map_order else (mpad, "scatter")
+        hit = self._perm_cache.get(key)
+        if hit is not None:
+            return hit
+        if map_order:
+            stride = 0
+            proto_of_col = np.arange(mpad, dtype=np.int32)
+            proto_of_col[:m] = self._map_order
+        else:
+            stride = scatter_stride(mpad)
+            proto_of_col = ((np.arange(mpad, dtype=np.int64) * stride) % mpad).astype(np.int32)
+            if mpad > 65535:
+                stride = 0
+            if os.environ.get("DBGSOM_PERM") == "random":  # tuning switch
+                proto_of_col = np.random.default_rng(0x5EED + mpad).permutation(mpad).astype(np.int32)
+                stride = 0
+            if os.environ.get("DBGSOM_PERM") == "table":
+                stride = 0
+        col_of_proto = np.empty_like(proto_of_col)
+        col_of_proto[proto_of_col] = np.arange(mpad, dtype=np.int32)
+        hit = (torch.from_numpy(proto_of_col).to(self.dev), torch.from_numpy(col_of_proto).to(self.dev), stride)
+        if len(self._perm_cache) > 8:
+            self._perm_cache.clear()
+        self._perm_cache[key] = hit
+        return hit
+
+    def _prepare_w(self, W, m: int, tensor: bool, need_lo: bool, top1: bool = True, map_order: bool = False) -> int:
         torch = self.torch
         mpad = _round_up(m, 256)
         if tensor:
-            if getattr(self, "_perm_mpad", None) != mpad:
-                # fixed scattered visiting order of the shadow rows (see bmu_tc.cu): shadow row c holds
-                # prototype (c * stride) % mpad, stride ~ mpad / golden ratio and coprime to mpad -- a
-                # low-discrepancy sequence over the map that the kernel can evaluate in registers
-                stride = scatter_stride(mpad)
-                self.proto_stride = stride if mpad <= 65535 else 0
-                proto_of_col = ((np.arange(mpad, dtype=np.int64) * stride) % mpad).astype(np.int32)
-                if os.environ.get("DBGSOM_PERM") == "random":  # tuning switch
-                    proto_of_col = np.random.default_rng(0x5EED + mpad).permutation(mpad).astype(np.int32)
-                    self.proto_stride = 0
-                if os.environ.get("DBGSOM_PERM") == "table":
-                    self.proto_stride = 0
-                col_of_proto = np.empty_like(proto_of_col)
-                col_of_proto[proto_of_col] = np.arange(mpad, dtype=np.int32)
-                self.proto_of_col = torch.from_numpy(proto_of_col).to(self.dev)
-                self.col_of_proto = torch.from_numpy(col_of_proto).to(self.dev)
-                self._perm_mpad = mpad
+            self.proto_of_col, self.col_of_proto, self.proto_stride = self._column_order(m, mpad, map_order)
             if self.W16_hi is None or self.W16_hi.shape[0] < mpad or (need_lo and self.W16_lo is None):
                 rows = _round_up(max(mpad, self.cap), 256)
                 self.W16_hi = torch.zeros((rows, self.ld16), dtype=torch.float16, device=self.dev)
@@ -495,17 +543,32 @@ class DeviceEngine:
         return mpad
 
     def _run_bmu(self, X, n: int, ldx: int, x16, W, m: int, n_bmu: int, want_dist: bool, idx, dist, backend=None,
-                 strict=None):
+                 strict=None, row_perm=None, selective=False):
         """prepare_w + candidate search + exact re-score for samples X against prototypes W."""
         be, n_pass = self._pick_backend(n, m) if backend is None else backend
         if W.shape[0] > self.W32.shape[0]:
             self.W32 = self.torch.zeros((W.shape[0], self.ldx), dtype=self.torch.float32, device=self.dev)
         with self._Phase(self, "prepare_w"):
-            mpad = self._prepare_w(W, m, be == nat.BMU_TENSOR, n_pass == 3, top1=n_bmu == 1)
-        self._bmu_search(X, n, ldx, x16, W, m, mpad, n_bmu, want_dist, idx, dist, (be, n_pass), strict=strict)
+            mpad = self._prepare_w(W, m, be == nat.BMU_TENSOR, n_pass == 3, top1=n_bmu == 1, map_order=selective)
+        self._bmu_search(X, n, ldx, x16, W, m, mpad, n_bmu, want_dist, idx, dist, (be, n_pass), strict=strict,
+                         row_perm=row_perm, selective=selective)
 
-    def _bmu_search(self, X, n, ldx, x16, W, m, mpad, n_bmu, want_dist, idx, dist, backend, ws_key="bmu", strict=None):
-        """Candidate search + exact re-score of n sample rows (shadows of W must be current)."""
+    def _select_eligible(self, n: int, m: int, backend) -> bool:
+        """The selective search applies: tensor search with three passes, one winner, shapes the kernels cover, and a
+        topology to order the shadow columns by."""
+        if not self.select_enabled or backend != (nat.BMU_TENSOR, 3):
+            return False
+        if self._map_order is None or len(self._map_order) != m:
+            return False
+        return bool(self.lib.dbgsom_bmu_select_supported(n, self.ld16, _round_up(m, 256), 1, self.select_granule))
+
+    def _bmu_search(self, X, n, ldx, x16, W, m, mpad, n_bmu, want_dist, idx, dist, backend, ws_key="bmu", strict=None,
+                    row_perm=None, selective=False):
+        """Candidate search + exact re-score of n sample rows (shadows of W must be current).
+
+        `row_perm`: the shadows are in sorted sample order.  `selective`: FLAG pass (one fp16 pass, which column tiles
+        can hold the winner of which row-tile pair) + REFINE pass (three passes over those tiles) instead of the
+        classic three passes over everything; needs row_perm and the map-patch column order."""
         be, n_pass = backend
         tensor = be == nat.BMU_TENSOR
         ws_bytes = self.lib.dbgsom_bmu_workspace_bytes(n, n_bmu)
@@ -530,8 +593,28 @@ class DeviceEngine:
         a.d_idx, a.d_dist = idx.data_ptr(), (dist.data_ptr() if dist is not None else None)
         a.d_stats = self.bmu_stats.data_ptr()
         a.d_workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
-        with self._Phase(self, "bmu_candidates"):
-            nat.check(self.lib.dbgsom_bmu_candidates(a, self._stream()), "dbgsom_bmu_candidates")
+        if tensor and row_perm is not None:
+            a.d_row_perm = row_perm.data_ptr()
+        if selective:
+            n_pairs = -(-(-(-n // 128)) // 2)
+            if self.tile_mask is None or self.tile_mask.numel() < n_pairs:
+                self.tile_mask = self.torch.zeros(n_pairs, dtype=self.torch.int64, device=self.dev)
+            self.tile_mask.zero_()
+            a.d_tile_mask = self.tile_mask.data_ptr()
+            a.select_granule = self.select_granule
+            a.select, a.n_pass = nat.SELECT_FLAG, 1
+            with self._Phase(self, "bmu_candidates"):
+                nat.check(self.lib.dbgsom_bmu_candidates(a, self._stream()), "dbgsom_bmu_candidates[flag]")
+            a.select, a.n_pass = nat.SELECT_REFINE, 3
+            with self._Phase(self, "bmu_second_stage"):
+                nat.check(self.lib.dbgsom_bmu_candidates(a, self._stream()), "dbgsom_bmu_candidates[refine]")
+            self.launches += 2
+            self._epoch_kinds["selective"] += 1
+        else:
+            if tensor and n_pass == 3 and n_bmu == 1:
+                self._epoch_kinds["classic"] += 1
+            with self._Phase(self, "bmu_candidates"):
+                nat.check(self.lib.dbgsom_bmu_candidates(a, self._stream()), "dbgsom_bmu_candidates")
         with self._Phase(self, "bmu_resolve"):
             nat.check(self.lib.dbgsom_bmu_resolve(a, self._stream()), "dbgsom_bmu_resolve")
         self.launches += 4  # candidate kernel, queue memset, re-score kernel, re-scan kernel
@@ -550,6 +633,7 @@ class DeviceEngine:
             be = self._pick_backend(self.N, m)
             tensor = be[0] == nat.BMU_TENSOR
             need_lo = be[1] == 3
+            self.row_perm = None  # the shadows are rebuilt chunk by chunk in natural sample order
             if tensor and (self.X16_hi is None or (need_lo and self.X16_lo is None)):
                 self.X16_hi = torch.empty((self.N, self.ld16), dtype=torch.float16, device=self.dev)
                 self.X16_lo = torch.empty((self.N, self.ld16), dtype=torch.float16, device=self.dev) if need_lo else None
@@ -595,10 +679,34 @@ class DeviceEngine:
                 self._ensure_x16(be[1] == 3)
                 x16 = (self.X16_hi, self.X16_lo, self.xnorm16)
             idx = self.idx.view(-1)[: self.N]
-            self._run_bmu(self.X, self.N, self.ldx, x16, cur, m, 1, False, idx, None, backend=be)
-            return self._update_and_smooth(be, idx, sigma, pack_rows, entropy_error)
+            eligible = self._select_eligible(self.N, m, be)
+            # the selective search needs the sorted sample order, i.e. the winners of an earlier epoch
+            selective = eligible and self.row_perm is not None
+            self._run_bmu(self.X, self.N, self.ldx, x16, cur, m, 1, False, idx, None, backend=be,
+                          row_perm=self.row_perm if be[0] == nat.BMU_TENSOR else None, selective=selective)
+            return self._update_and_smooth(be, idx, sigma, pack_rows, entropy_error, resort=eligible)
 
-    def _update_and_smooth(self, be, idx, sigma: float, pack_rows: bool, entropy_error: bool) -> dict:
+    def _resort_samples(self, idx, m: int, acc_ws) -> None:
+        """Rebuild the fp16 shadows in the order K2 has just grouped the samples in (by winner, ascending index): row
+        tiles of the tensor search then hold samples that compete for the same few prototypes.  One pass over X."""
+        torch = self.torch
+        off = int(self.lib.dbgsom_accumulate_perm_offset(self.N, m))
+        perm = acc_ws[off : off + 4 * self.N].view(torch.int32)
+        if self.row_perm is None:
+            self.row_perm = torch.empty(self.N, dtype=torch.int32, device=self.dev)
+        self.row_perm.copy_(perm)
+        nat.check(
+            self.lib.dbgsom_prepare_x16_sorted(
+                self.X.data_ptr(), self.N, self.ldx, self.ldx, self.shift.data_ptr(), self.scale, self.row_perm.data_ptr(),
+                self.X16_hi.data_ptr(), self.X16_lo.data_ptr() if self.X16_lo is not None else None, self.ld16,
+                self.xnorm16.data_ptr(), self._stream(),
+            ),
+            "dbgsom_prepare_x16_sorted",
+        )
+        self.launches += 2
+        self._sort_age = 0
+
+    def _update_and_smooth(self, be, idx, sigma: float, pack_rows: bool, entropy_error: bool, resort: bool = False) -> dict:
         """K2 -> all-reduce -> K3 -> read-back, given the winners of the current prototypes."""
         torch = self.torch
         m, cur = self.M, self.W[self.cur]
@@ -618,6 +726,11 @@ class DeviceEngine:
         with self._Phase(self, "accumulate"):
             nat.check(self.lib.dbgsom_accumulate(acc, self._stream()), "dbgsom_accumulate")
         self.launches += 6 + (1 if use_hist else 0)
+        if resort and self.X16_hi is not None:
+            self._sort_age += 1
+            if self.row_perm is None or self._sort_age >= self.resort_every:
+                with self._Phase(self, "resort"):
+                    self._resort_samples(idx, m, ws)
 
         # the one collective of the path: per-neuron partial sums (+ class histogram)
         with self._Phase(self, "allreduce"):
@@ -683,9 +796,20 @@ class DeviceEngine:
         if reset:
             self.bmu_stats.zero_()
         out = {"ambiguous": int(s[0]), "flagged": int(s[1]), "candidates": int(s[2]), "full_rescans": int(s[3]),
-               "fp32_reruns": int(self.fp32_reruns)}
+               "refined_tiles": int(s[4]), "row_tile_pairs": int(s[5]), "fp32_reruns": int(self.fp32_reruns),
+               "selective_searches": self._epoch_kinds["selective"], "classic_searches": self._epoch_kinds["classic"]}
+        # MMA work of the top-1 three-pass searches in units of one fp16 pass over all (sample, prototype) pairs:
+        # classic = 3; selective = 1 (FLAG pass) + 3 x the share of (row-tile pair, column tile) products refined
+        n_sel, n_cls = out["selective_searches"], out["classic_searches"]
+        if n_sel + n_cls:
+            share = 0.0
+            if s[5] > 0 and self.M > 0:
+                share = float(s[4]) * self.select_granule / (float(s[5]) * _round_up(self.M, 256))
+            out["refined_share"] = share
+            out["mma_passes"] = (n_sel * (1.0 + 3.0 * share) + 3.0 * n_cls) / (n_sel + n_cls)
         if reset:
             self.fp32_reruns = 0
+            self._epoch_kinds = {"selective": 0, "classic": 0}
         return out
 
     def bmu_train(self, n_bmu: int, previous: bool = False):
@@ -702,7 +826,8 @@ class DeviceEngine:
                 x16 = (self.X16_hi, self.X16_lo, self.xnorm16)
             idx = torch.empty((self.N, n_bmu), dtype=torch.int32, device=self.dev)
             dist = torch.empty((self.N, n_bmu), dtype=torch.float64, device=self.dev)
-            self._run_bmu(self.X, self.N, self.ldx, x16, W, m, n_bmu, True, idx, dist, backend=be)
+            self._run_bmu(self.X, self.N, self.ldx, x16, W, m, n_bmu, True, idx, dist, backend=be,
+                          row_perm=self.row_perm if be[0] == nat.BMU_TENSOR else None)
             return dist.cpu().numpy(), idx.cpu().numpy().astype(np.int64)
 
     # ------------------------------------------------------------------ post-training passes
@@ -720,7 +845,8 @@ class DeviceEngine:
         idx = torch.empty((self.N, n_bmu), dtype=torch.int32, device=self.dev)
         dist = torch.empty((self.N, n_bmu), dtype=torch.float64, device=self.dev)
         # the post-training passes run once per fit: flagged samples are always re-scored against all prototypes
-        self._run_bmu(self.X, self.N, self.ldx, x16, W, m, n_bmu, True, idx, dist, backend=be, strict=True)
+        self._run_bmu(self.X, self.N, self.ldx, x16, W, m, n_bmu, True, idx, dist, backend=be, strict=True,
+                      row_perm=self.row_perm if be[0] == nat.BMU_TENSOR else None)
         return idx, dist, m
 
     def final_statistics(self, positions: np.ndarray, degrees: np.ndarray) -> dict:
@@ -806,6 +932,7 @@ class DeviceEngine:
             self.ldx = int(self.X.shape[1])
             self.ld16 = _round_up(self.ldx, 64)
             self.labels, self.n_classes = None, 0
+            self.row_perm = None
             self.W = None
             self._alloc_map(W.shape[0])
             self.cur = 0

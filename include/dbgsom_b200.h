@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define DBGSOM_ABI_VERSION 6
+#define DBGSOM_ABI_VERSION 7
 
 #define DBGSOM_OK 0
 #define DBGSOM_E_BADARG (-1)      /* null pointer, non-positive size, bad enum             */
@@ -82,6 +82,14 @@ int dbgsom_colstats(const float* d_X, int64_t N, int D, int64_t ldx, const float
 int dbgsom_prepare_x16(const float* d_X, int64_t N, int D, int64_t ldx, const float* d_shift /*[D]*/,
                        float scale, uint16_t* d_X16_hi, uint16_t* d_X16_lo, int64_t ld16,
                        float* d_xnorm16 /*[N]*/, void* stream);
+
+/* Same, with the shadow rows in a caller-given order: shadow row p is built from sample d_perm[p] (a permutation of
+ * 0..N-1, e.g. the samples grouped by winner that dbgsom_accumulate leaves in its workspace, see
+ * dbgsom_accumulate_perm_offset); d_xnorm16 stays indexed by SAMPLE.  Pass the permutation to the search as
+ * dbgsom_bmu_args.d_row_perm. */
+int dbgsom_prepare_x16_sorted(const float* d_X, int64_t N, int D, int64_t ldx, const float* d_shift, float scale,
+                              const int32_t* d_perm, uint16_t* d_X16_hi, uint16_t* d_X16_lo, int64_t ld16,
+                              float* d_xnorm16, void* stream);
 
 /* W (float64 master) -> W32, and optionally the fp16 shadow of the tensor back end.
  * With c = mean_j W[j,:] (written to d_wshift, float64 [D]), u_j = (w_j - c) * scale and
@@ -184,12 +192,37 @@ typedef struct dbgsom_bmu_args {
   /* outputs */
   int32_t* d_idx;          /* [N, n_bmu] winners, ascending distance */
   double* d_dist;          /* [N, n_bmu] Euclidean distances (want_dist=1), else may be NULL */
-  int64_t* d_stats;        /* optional [4], atomically incremented: #samples with more candidates than
-                              n_bmu, #flagged samples, #candidates re-scored, #full re-scores */
+  int64_t* d_stats;        /* optional [8], atomically incremented: #samples with more candidates than
+                              n_bmu, #flagged samples, #candidates re-scored, #full re-scores, and by the selective
+                              search (below) #(row-tile pair, column tile) products refined, #row-tile pairs,
+                              column tiles per row-tile pair; [7] reserved */
   /* scratch */
   void* d_workspace;
   size_t workspace_bytes;
+  /* sorted sample order + selective search (tensor back end, n_bmu = 1; all optional, zero = off).
+   * d_row_perm: the fp16 shadows were built by dbgsom_prepare_x16_sorted, i.e. shadow row p belongs to sample
+   * d_row_perm[p]; every per-sample output (d_idx, the candidate table) is written at the sample's own index.
+   * select = DBGSOM_SELECT_FLAG runs ONE fp16 pass (bound of n_pass = 1) over all prototypes and only records, per
+   * pair of 128-row tiles, which column tiles of `select_granule` prototypes hold a score within the one-pass bound
+   * of the smallest one-pass score of any of its rows (bit c of d_tile_mask[pair], OR-ed in: zero the masks first).
+   * select = DBGSOM_SELECT_REFINE runs the three-pass candidate search of n_pass = 3 over exactly those column tiles.
+   * The exact winner's one-pass score is within twice the one-pass error bound of the row's best one-pass score, so
+   * its column tile is always refined; with the rows sorted by their previous winner and the shadow columns laid
+   * out in map patches a row-tile pair touches few column tiles. */
+  const int32_t* d_row_perm;      /* [N] or NULL */
+  uint64_t* d_tile_mask;          /* [ceil(ceil(N / 128) / 2)] */
+  const void* reserved0;          /* must be NULL */
+  int32_t select;                 /* DBGSOM_SELECT_OFF / _FLAG / _REFINE */
+  int32_t select_granule;         /* 64 or 128 prototypes per mask bit; Mpad / granule <= 64 */
 } dbgsom_bmu_args;
+
+#define DBGSOM_SELECT_OFF 0
+#define DBGSOM_SELECT_FLAG 1
+#define DBGSOM_SELECT_REFINE 2
+
+/* 1 if the selective search (select != 0) is implemented for these shapes (D <= 256 after padding, at least one
+ * row tile per SM, Mpad <= 4096 and Mpad / select_granule <= 64, n_bmu = 1), else 0. */
+int dbgsom_bmu_select_supported(int64_t N, int64_t ld16, int32_t Mpad, int32_t n_bmu, int32_t select_granule);
 
 size_t dbgsom_bmu_workspace_bytes(int64_t N, int32_t n_bmu);
 int dbgsom_bmu(const dbgsom_bmu_args* args, void* stream);
@@ -232,6 +265,9 @@ typedef struct dbgsom_accumulate_args {
 } dbgsom_accumulate_args;
 
 size_t dbgsom_accumulate_workspace_bytes(int64_t N, int32_t M);
+/* Byte offset, inside the workspace of dbgsom_accumulate(N, M), of the int32 [N] sample permutation grouped by
+ * winner (ascending winner index) that the call leaves behind. */
+size_t dbgsom_accumulate_perm_offset(int64_t N, int32_t M);
 int dbgsom_accumulate(const dbgsom_accumulate_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -57,9 +57,30 @@ def test_argument_errors_do_not_touch_the_gpu(lib):
 
 def test_struct_sizes_match_the_c_layout():
     # 64-bit layout of the three argument structs (guards against field drift in the binding)
-    assert ctypes.sizeof(nat.BmuArgs) == 224
+    assert ctypes.sizeof(nat.BmuArgs) == 256
     assert ctypes.sizeof(nat.AccumulateArgs) == 112
     assert ctypes.sizeof(nat.SmoothArgs) == 96
+
+
+def test_struct_sizes_match_the_header_as_compiled(tmp_path):
+    """sizeof() of the argument structs as a C compiler lays out include/dbgsom_b200.h == the ctypes mirror."""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "sizes.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "dbgsom_b200.h"\n'
+        'int main(void) { printf("%zu %zu %zu %d\\n", sizeof(dbgsom_bmu_args), sizeof(dbgsom_accumulate_args), '
+        "sizeof(dbgsom_smooth_args), DBGSOM_ABI_VERSION); return 0; }\n"
+    )
+    exe = tmp_path / "sizes"
+    subprocess.run(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    assert [int(v) for v in out] == [ctypes.sizeof(nat.BmuArgs), ctypes.sizeof(nat.AccumulateArgs),
+                                     ctypes.sizeof(nat.SmoothArgs), nat.ABI_VERSION]
 
 
 def test_engine_refuses_to_run_without_cuda():

@@ -880,11 +880,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
         asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
       }
-    } else
+    } else {
+    // sample index and norm of my row in the NEXT row tile are fetched one row tile ahead: two dependent global loads
+    // (permutation, then norm) that otherwise stall every epilogue warp at the start of every row tile -- with the
+    // ~10 column tiles per row tile of a REFINE pass that was a fifth of its time
+    int64_t orow_next = 0;
+    float xn_next = 0.f;
+    auto fetch_row = [&](int64_t it_) {
+      const int64_t r_ = it_ < n_iters ? tile_of(it_) * BM + t : N;
+      orow_next = r_ < N ? (row_perm ? (int64_t)row_perm[r_] : r_) : 0;
+      xn_next = r_ < N ? xnorm16[orow_next] : 0.f;
+    };
+    fetch_row(0);
     for (int64_t it = 0; it < n_iters; ++it) {
       const int64_t row = tile_of(it) * BM + t;
-      const int64_t orow = row < N ? (row_perm ? (int64_t)row_perm[row] : row) : 0;
-      const float tau = row < N ? 2.f * tensor_score_bound(xnorm16[orow], wmax, bound_coef, acc_coef) : 0.f;
+      const int64_t orow = orow_next;
+      const float tau = row < N ? 2.f * tensor_score_bound(xn_next, wmax, bound_coef, acc_coef) : 0.f;
+      fetch_row(it + 1);
       float m1 = kInf, m2 = kInf, thr = kInf, evicted = __int_as_float(0x7f800000);
       float gate = __int_as_float(0x7f800000);  // fast gate of my table (see slow_offer); +inf while a slot is free
       asm volatile("st.shared.v4.f32 [%0], {%1,%1,%1,%1};" ::"r"(my_val_addr), "f"(gate) : "memory");
@@ -1065,42 +1077,52 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
         const float gm = NB == 1 ? g1 : g2;
         const float gthr = gm < 1.0e38f ? gm + tau : kInf;
-        int out[kMaxCand];
+        // the sixteen (score, prototype) pairs of the row: independent loads first, then branch-free bookkeeping
+        float v[EPI_SUBS * KSUB];
+        int jx[EPI_SUBS * KSUB];
+#pragma unroll
+        for (int q = 0; q < EPI_SUBS; ++q) {
+          const float4 v4 = lds_f4(smem_u32(tab_val + (t * EPI_SUBS + q) * KSUB));
+          const int4 j4 = lds_i4(smem_u32(tab_idx + (t * EPI_SUBS + q) * KSUB));
+          v[4 * q + 0] = v4.x; v[4 * q + 1] = v4.y; v[4 * q + 2] = v4.z; v[4 * q + 3] = v4.w;
+          jx[4 * q + 0] = j4.x; jx[4 * q + 1] = j4.y; jx[4 * q + 2] = j4.z; jx[4 * q + 3] = j4.w;
+        }
         int cnt = 0, best = -1;
         float bv = __int_as_float(0x7f800000), sv = __int_as_float(0x7f800000);  // two smallest scores kept
         bool overflow = ev <= gthr;
-#pragma unroll 1
-        for (int q = 0; q < EPI_SUBS; ++q) {
-          for (int e = 0; e < KSUB; ++e) {
-            const float v = tab_val[(t * EPI_SUBS + q) * KSUB + e];
-            if (v <= gthr) {  // free slots hold +inf, gthr is finite
-              const int jj = tab_idx[(t * EPI_SUBS + q) * KSUB + e];
-              if (cnt < kMaxCand) out[cnt] = jj;
-              ++cnt;
-              if (v < bv || (v == bv && jj < best)) {
-                sv = bv;
-                bv = v;
-                best = jj;
-              } else if (v < sv) {
-                sv = v;
-              }
-            }
-          }
+#pragma unroll
+        for (int i = 0; i < EPI_SUBS * KSUB; ++i) {
+          const bool in = v[i] <= gthr;  // free slots hold +inf, gthr is finite
+          const bool first = in && (v[i] < bv || (v[i] == bv && jx[i] < best));
+          const bool second = in && !first && v[i] < sv;
+          cnt += in ? 1 : 0;
+          sv = first ? bv : (second ? v[i] : sv);
+          bv = first ? v[i] : bv;
+          best = first ? jx[i] : best;
         }
         if (cnt > kMaxCand) overflow = true;
         if (row < N) {
-          const int valid = overflow ? 0 : cnt;
+          // candidate slots past the count are never read (bmu_resolve.cu); a row with one candidate -- almost all of
+          // them -- writes one slot.  A flagged row has no candidate list; its first slot carries the gap between the
+          // two smallest approximate scores instead (>= 0, float bits), which tightens the near-tie test of the re-score
+          int32_t* slots = cand_idx + orow * kMaxCand;
+          if (overflow) {
+            slots[0] = __float_as_int(fmaxf(sv - bv, 0.f));
+          } else if (cnt == 1) {
+            slots[0] = best;
+          } else {
+            int w = 0;
 #pragma unroll
-          for (int q = 0; q < kMaxCand; ++q) cand_idx[orow * kMaxCand + q] = q < valid ? out[q] : -1;
-          // a flagged row has no candidate list; its first slot carries the gap between the two smallest
-          // approximate scores instead (>= 0, float bits), which tightens the near-tie test of the re-score
-          if (overflow) cand_idx[orow * kMaxCand] = __float_as_int(fmaxf(sv - bv, 0.f));
+            for (int i = 0; i < EPI_SUBS * KSUB; ++i)
+              if (v[i] <= gthr) slots[w++] = jx[i];
+          }
           cand_count[orow] = (uint8_t)(overflow ? DBGSOM_CAND_OVERFLOW : cnt);
           idx_out[orow * NB] = best;
         }
         row_min[t] = kInf;
       }
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
+    }
     }
   }
 

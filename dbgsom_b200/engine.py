@@ -268,6 +268,19 @@ class DeviceEngine:
         self.total_variance = stats["total_variance"]
         # data mean (centres the fp16 shadow) and a power-of-two scale that keeps it in range
         mean = shift_row.double().cpu().numpy() + s1 / self.n_samples_global
+        # the device copy of X is float32: an offset far larger than the spread costs that many digits of the spread
+        n_g = self.n_samples_global
+        std = np.sqrt(np.maximum(s2 - s1 * s1 / n_g, 0.0) / max(n_g, 1))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ratio = np.where(std > 0, np.abs(mean) / std, 0.0)
+        if ratio.size and float(ratio.max()) > 1e3:
+            import warnings
+
+            warnings.warn(
+                f"column {int(ratio.argmax())} has |mean| / std = {float(ratio.max()):.3g}: samples are stored as float32 on the "
+                "device, so about that many digits of the column's spread are lost; centre the data before fitting",
+                RuntimeWarning, stacklevel=3,
+            )
         self.shift = torch.from_numpy(mean.astype(np.float32)).to(self.dev)
         # |x'| <= 2^12 leaves a factor 16 of fp16 range for prototypes outside the data hull
         self.scale = 1.0 if not (maxabs > 0 and math.isfinite(maxabs)) else 2.0 ** math.floor(
@@ -559,6 +572,8 @@ class DeviceEngine:
         if not self.select_enabled or backend != (nat.BMU_TENSOR, 3):
             return False
         if self._map_order is None or len(self._map_order) != m:
+            return False
+        if _round_up(m, 256) < 1024:  # a handful of column tiles: nothing to select from
             return False
         return bool(self.lib.dbgsom_bmu_select_supported(n, self.ld16, _round_up(m, 256), 1, self.select_granule))
 

@@ -41,7 +41,7 @@ def main():
     rank, world = dist.get_rank(), dist.get_world_size()
     n, d, c = 80000, 96, 5
     X, y = _datasets.gmm(n, d, c, 7, return_labels=True)
-    topo = MapTopology.full_grid(12, 12)  # >= 128 prototypes: the tcgen05 search (MR_BACKEND=tensor) applies
+    topo = MapTopology.full_grid(32, 32)  # 1024 prototypes: the tcgen05 search incl. its selective form applies
     rows = np.random.default_rng(0).choice(n, len(topo), replace=False)
     sigmas = [2.0, 1.6, 1.2]
     per = -(-n // world)
@@ -71,7 +71,9 @@ def main():
         for e_, (r, win, s) in enumerate(zip(outs, wins, sigmas)):
             _, ref_win, gap = O.bmu_with_gap(X64, r["W_in"])
             strict = gap >= 1e-6
-            assert strict.mean() > 0.95 and np.array_equal(win[strict], ref_win[strict]), f"epoch {e_}"
+            bad = np.flatnonzero((win != ref_win) & strict)
+            assert strict.mean() > 0.5, f"epoch {e_}: only {strict.mean():.3f} of the samples outside the near-tie gate"
+            assert bad.size == 0, f"epoch {e_}: {bad.size} winners differ outside the gate, rows {bad[:5]}, gaps {gap[bad[:5]]}"
             ref = O.epoch_step(X64, r["W_in"], hop, s, V, pack=True, winners=win)
             np.testing.assert_array_equal(r["counts"], ref["n"])
             np.testing.assert_allclose(r["error"], ref["E"], rtol=1e-5, atol=1e-6)
@@ -89,10 +91,21 @@ def main():
         np.testing.assert_allclose(W, r_W, rtol=1e-10, atol=1e-12)
         for k in ("te_count", "qe_sum"):
             assert abs(st[k] - r_st[k]) <= 1e-10 * max(1.0, abs(r_st[k])), k
-        np.testing.assert_array_equal(st["hits"], r_st["hits"])
-        np.testing.assert_allclose(st["dens_sum"], r_st["dens_sum"], rtol=1e-9)
-        np.testing.assert_array_equal(hist[0], r_hist[0])
-        np.testing.assert_array_equal(hist[1], r_hist[1])
+        _, _, gap_prev = O.bmu_with_gap(X64, outs[-1]["W_in"])
+        near_prev = int((gap_prev < 1e-9).sum())
+        assert np.abs(st["hits"] - r_st["hits"]).sum() <= 2 * near_prev
+        if near_prev == 0:
+            np.testing.assert_allclose(st["dens_sum"], r_st["dens_sum"], rtol=1e-9)
+        else:
+            assert abs(st["dens_sum"].sum() - r_st["dens_sum"].sum()) <= 1e-6 * abs(r_st["dens_sum"].sum())
+        # label histogram of the final top-1 search: the sharded and the single-GPU prototypes agree to ~1e-12, so only
+        # samples sitting between prototypes that are (nearly) exact copies may land in another cell
+        _, _, gap_final = O.bmu_with_gap(X64, W)
+        near = int((gap_final < 1e-9).sum())
+        assert np.abs(hist[0] - r_hist[0]).sum() <= 2 * near, (np.abs(hist[0] - r_hist[0]).sum(), near)
+        assert hist[0].sum() == r_hist[0].sum() == n
+        if near == 0:
+            np.testing.assert_array_equal(hist[1], r_hist[1])
         print("MULTIRANK_OK world=%d shard_min_work=%s" % (world, os.environ.get("DBGSOM_K3_SHARD_MIN_WORK")), flush=True)
     dist.barrier()
     dist.destroy_process_group()

@@ -31,7 +31,7 @@ def patch_ids(side, ph, pw, dev):
 
 
 @torch.no_grad()
-def analyse(X, W, prev_win, shift, scale, side, tag, coef=0.25 * 2.0**-9, acc=2.4e-7):
+def analyse(X, W, prev_win, shift, scale, side, tag, coef=0.25 * 2.0**-9, acc=2.4e-7, prev_dirty=None):
     dev = X.device
     n, d = X.shape
     m = W.shape[0]
@@ -44,8 +44,11 @@ def analyse(X, W, prev_win, shift, scale, side, tag, coef=0.25 * 2.0**-9, acc=2.
     tiles = {"128 (8x16)": patch_ids(side, 8, 16, dev), "64 (8x8)": patch_ids(side, 8, 8, dev), "32 (4x8)": patch_ids(side, 4, 8, dev)}
     # sort rows by the column tile, then the index, of their previous winner
     key = tiles["128 (8x16)"][prev_win] * m + prev_win
+    if prev_dirty is not None:  # minor key: how many candidates the row had in the previous search (0: 1, 1: 2-8, 2: 9-64, 3: more)
+        bucket = (prev_dirty > 1).long() + (prev_dirty > 8).long() + (prev_dirty > 64).long()
+        key = key * 4 + bucket
     order = torch.argsort(key)
-    chunk = 1 << 17
+    chunk = (1 << 17) if m <= 4096 else (1 << 14)
     ncand = torch.empty(n, dtype=torch.int32, device=dev)
     masks = {k: torch.zeros((n, int(t.max()) + 1), dtype=torch.bool, device=dev) for k, t in tiles.items()}
     for s in range(0, n, chunk):
@@ -79,12 +82,16 @@ def analyse(X, W, prev_win, shift, scale, side, tag, coef=0.25 * 2.0**-9, acc=2.
     inv[order] = torch.arange(n, device=dev)
     w32o = masks["32 (4x8)"][inv][: n // 32 * 32].view(n // 32, 32, -1).any(dim=1)
     print(f"   unsorted rows: {w32o.float().mean():.3f}")
+    out = torch.empty_like(ncand)
+    out[order] = ncand
+    return out  # candidates per row, in sample order
 
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 2_000_000
     epochs = int(sys.argv[2]) if len(sys.argv) > 2 else 13
-    side, d = 64, 256
+    d = int(sys.argv[3]) if len(sys.argv) > 3 else 256
+    side = int(sys.argv[4]) if len(sys.argv) > 4 else 64
     m = side * side
     dev = torch.device("cuda", 0)
     X = make_shard(torch, dev, n, d, 64, 0)
@@ -95,7 +102,14 @@ def main():
     hist = []
     for e in range(epochs):
         W = eng.W[eng.cur][:m].clone()
-        if e in (2, 4, 8, 12) and hist:
+        if e in (7, 8, 11, 12) and hist and os.environ.get("STUDY_DIRTY"):
+            if e in (7, 11):
+                dirty = analyse(X, W, hist[-1], eng.shift, eng.scale, side, f"epoch {e} (dirtiness source)")
+            else:
+                analyse(X, W, hist[-1], eng.shift, eng.scale, side, f"epoch {e}, sorted by winner only")
+                analyse(X, W, hist[-1], eng.shift, eng.scale, side, f"epoch {e}, sorted by (winner, candidate-count bucket of epoch {e - 1})",
+                        prev_dirty=dirty)
+        elif e in (2, 4, 8, 12) and hist:
             analyse(X, W, hist[-1], eng.shift, eng.scale, side, f"epoch {e}, rows sorted by the winners of epoch {e - 1}")
             if len(hist) >= 4:
                 analyse(X, W, hist[-4], eng.shift, eng.scale, side, f"epoch {e}, rows sorted by the winners of epoch {e - 4}")

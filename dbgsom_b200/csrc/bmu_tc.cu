@@ -517,8 +517,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       int stage = 0;
       uint32_t phase = 0, a_phase = 0;
       unsigned long long sel_tiles = 0, sel_pairs = 0;
+      unsigned long long pmask_next = SEL == 2 ? sel_mask(0) : 0ull;
       for (int64_t it = 0; it < n_iters; ++it) {
         const int row0 = (int)(tile_of(it) * BM);
+        const unsigned long long pmask_it = pmask_next;
+        if (SEL == 2) pmask_next = it + 1 < n_iters ? sel_mask(it + 1) : 0ull;
         if (XRES) {
           mbar_wait(&bars->a_empty, a_phase ^ 1);
           mbar_expect_tx(&bars->a_full, (uint32_t)(KB * C::NA * A_TILE_BYTES));
@@ -555,7 +558,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             }
           }
         }
-        unsigned long long selm = sel_mask(it);
+        unsigned long long selm = pmask_it;
         const int n_sel = SEL == 2 ? __popcll(selm) : NT;
         if (SEL == 2 && cl_rank == 0 && pair_of(it) < n_pairs) {
           sel_tiles += (unsigned)n_sel;
@@ -632,7 +635,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       constexpr uint32_t idesc = instr_desc_f16(PAIR ? 2 * BM : BM, BN);
       int stage = 0;
       uint32_t phase = 0, a_phase = 0, acc = 0, acc_phase = 0;
+      unsigned long long mask_next = SEL == 2 ? sel_mask(0) : 0ull;  // the pair's mask is loaded one row tile ahead
       for (int64_t it = 0; it < n_iters; ++it) {
+        const unsigned long long mask_it = mask_next;
+        if (SEL == 2) mask_next = it + 1 < n_iters ? sel_mask(it + 1) : 0ull;
         if (XRES) {
           mbar_wait(&bars->a_full, a_phase);
           a_phase ^= 1;
@@ -676,7 +682,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             }
           }
         }
-        const int n_sel = SEL == 2 ? __popcll(sel_mask(it)) : NT;
+        const int n_sel = SEL == 2 ? __popcll(mask_it) : NT;
         for (int nt = 0; nt < n_sel; ++nt) {
           uint32_t tmem_d = tmem_base + acc * BN;
           if (!SEGM) {
@@ -881,27 +887,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
       }
     } else {
-    // sample index and norm of my row in the NEXT row tile are fetched one row tile ahead: two dependent global loads
-    // (permutation, then norm) that otherwise stall every epilogue warp at the start of every row tile -- with the
-    // ~10 column tiles per row tile of a REFINE pass that was a fifth of its time
-    int64_t orow_next = 0;
-    float xn_next = 0.f;
-    auto fetch_row = [&](int64_t it_) {
+    // Per row tile an epilogue thread needs its sample's index (through the permutation), the sample's norm (through that
+    // index) and the pair's column-tile mask: three global loads, two of them dependent, which stalled every epilogue
+    // warp at the start of every row tile (9 % of the REFINE pass's stall samples; it visits only ~10 column tiles per row
+    // tile).  They are software-pipelined: the index two row tiles ahead, norm and mask one row tile ahead -- no load
+    // is consumed in the iteration that issues it.
+    auto fetch_orow = [&](int64_t it_) -> int64_t {
       const int64_t r_ = it_ < n_iters ? tile_of(it_) * BM + t : N;
-      orow_next = r_ < N ? (row_perm ? (int64_t)row_perm[r_] : r_) : 0;
-      xn_next = r_ < N ? xnorm16[orow_next] : 0.f;
+      return r_ < N ? (row_perm ? (int64_t)row_perm[r_] : r_) : -1;
     };
-    fetch_row(0);
+    auto fetch_mask = [&](int64_t it_) -> unsigned long long { return it_ < n_iters ? sel_mask(it_) : 0ull; };
+    int64_t orow_n1 = fetch_orow(0);               // index of my row in row tile it + 1 (it = -1 here)
+    int64_t orow_n2 = fetch_orow(1);               //                                it + 2
+    float xn_n1 = orow_n1 >= 0 ? xnorm16[orow_n1] : 0.f;
+    unsigned long long mask_n1 = fetch_mask(0);
     for (int64_t it = 0; it < n_iters; ++it) {
       const int64_t row = tile_of(it) * BM + t;
-      const int64_t orow = orow_next;
-      const float tau = row < N ? 2.f * tensor_score_bound(xn_next, wmax, bound_coef, acc_coef) : 0.f;
-      fetch_row(it + 1);
+      const int64_t orow = orow_n1 >= 0 ? orow_n1 : 0;
+      const float tau = row < N ? 2.f * tensor_score_bound(xn_n1, wmax, bound_coef, acc_coef) : 0.f;
+      unsigned long long selm = mask_n1;
+      orow_n1 = orow_n2;
+      xn_n1 = orow_n1 >= 0 ? xnorm16[orow_n1] : 0.f;  // address known since the previous iteration
+      orow_n2 = fetch_orow(it + 2);
+      mask_n1 = fetch_mask(it + 1);
       float m1 = kInf, m2 = kInf, thr = kInf, evicted = __int_as_float(0x7f800000);
       float gate = __int_as_float(0x7f800000);  // fast gate of my table (see slow_offer); +inf while a slot is free
       asm volatile("st.shared.v4.f32 [%0], {%1,%1,%1,%1};" ::"r"(my_val_addr), "f"(gate) : "memory");
       asm volatile("st.shared.v4.s32 [%0], {%1,%1,%1,%1};" ::"r"(my_idx_addr), "r"(0x7fffffff) : "memory");
-      unsigned long long selm = sel_mask(it);
       const int n_sel = SEL == 2 ? __popcll(selm) : NT;
       for (int ti = 0; ti < n_sel; ++ti) {
         int nt = ti;

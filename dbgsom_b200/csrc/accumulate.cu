@@ -171,6 +171,7 @@ __global__ void __launch_bounds__(SCAT2_THREADS) scatter_chunk_kernel(const int3
 }
 
 // ------------------------------------------------------------------------------------------ accumulate
+constexpr int ACC_WIN_BYTES = (64 + 8) * 8 + 64;  // row-offset ring of a warp (+ mirror), padded to 640 bytes
 __device__ __forceinline__ uint32_t acc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // float -> double without the XU pipe.  ncu showed the first version of this kernel bound by
@@ -187,20 +188,6 @@ __device__ __forceinline__ double f32_as_f64(float f) {
   return __hiloint2double((int)hi, (int)(b << 29));
 }
 
-// Position of a warp in the sorted sample sequence: next position, its segment, the segment's end.
-struct SegCursor {
-  int32_t p, seg, seg_end;
-  // rows of the next batch: at most U, never across a segment boundary or the end of the range
-  __device__ __forceinline__ int next_batch(const int32_t* __restrict__ offsets, int32_t p_end, int U) {
-    while (p >= seg_end) {  // skip empty segments
-      ++seg;
-      seg_end = offsets[seg + 1];
-    }
-    const int32_t lim = p_end < seg_end ? p_end : seg_end;
-    return lim - p < U ? lim - p : U;
-  }
-};
-
 // VPL : float4 per lane per row slab;  WPR : warps cooperating on one row (team size);
 // U   : rows per batch (their sample weights are evaluated together, lane group u doing row u, so
 //       the float64 exp/sqrt costs 1/U per row);  STAGES : depth of the copy ring.
@@ -214,19 +201,29 @@ struct SegCursor {
 // Each element is converted to float64 ONCE and stays in registers (U * VPL * 4 doubles per lane) for
 // both uses -- the distance and, once the row's weight is known, the k * x sum: the first version
 // converted twice and was issue bound on the conversions (ncu: 69 % of the issue slots, 42 % of
-// DRAM peak).  The permutation entries of the next 64 positions are prefetched warp-wide.
+// DRAM peak).
+// Loop control (fourth version): the prefetch side owns the only cursor into the segment table.  It turns the
+// permutation into BYTE OFFSETS of the rows, 32 positions at a time (one coalesced load, fetched one window
+// ahead), in a 64-slot ring in shared memory, so that a row of a batch costs one broadcast ld.shared.u64 + one
+// 64-bit add + the copies; the rows-per-batch decision (never across a segment boundary) travels to the consuming
+// side through a byte FIFO in a register (bit 7 = "first batch of a segment").  The third version evaluated the
+// segment cursor twice and selected each row index with two shuffles out of a register window: ~160 of the 519
+// instructions per 4-row batch were loop control.
 // All arithmetic is float64: distances by direct differences, k = 1 - sqrt(1 - exp(-d^2 / V))
 // literally as dbgsom/BaseSom.py:536-537, sums in float64 registers.
-template <int VPL, int WPR, int U, int THREADS, int STAGES, bool FULLD>
+template <int VPL, int WPR, int U, int THREADS, int STAGES, bool FULLD, bool XU2>
 __global__ void __launch_bounds__(THREADS, 2) accumulate_kernel(
     const float* __restrict__ X, int64_t N, int D, int64_t ldx, const int32_t* __restrict__ perm,
     const int32_t* __restrict__ offsets, const double* __restrict__ W, int M, double inv_var,
     double* __restrict__ part) {
   constexpr int TEAMS = THREADS / 32 / WPR;
   constexpr int SLOT_BYTES = U * VPL * 512;          // one batch of one warp
-  constexpr int WARP_BYTES = STAGES * SLOT_BYTES + VPL * 1024;
+  constexpr int WARP_BYTES = STAGES * SLOT_BYTES + VPL * 1024 + ACC_WIN_BYTES;
   // per warp: [STAGES][U][VPL][32 lanes x 16 B] staged samples, then [VPL][32 lanes x 32 B] the current
-  // segment's float64 prototype (each lane keeps the 4 columns it owns; in registers it cost 16 of them)
+  // segment's float64 prototype (each lane keeps the 4 columns it owns; in registers it cost 16 of them),
+  // then the ring of row offsets: slot (p & 63) = byte offset of the row at position p; slots 0..7 are
+  // mirrored at 64..71 so a batch reads its <= 8 consecutive slots without wrapping
+  static_assert(U <= 8 && STAGES >= 2 && STAGES <= 4, "offset ring mirror / byte FIFO");
   extern __shared__ __align__(16) uint8_t stage_smem[];
   __shared__ double red[TEAMS][2][WPR][U];  // cross-warp partial squared distances (double buffered)
 
@@ -237,7 +234,7 @@ __global__ void __launch_bounds__(THREADS, 2) accumulate_kernel(
   const int col0 = tw * 128 * VPL + lane * 4;
   const int32_t total = offsets[M];  // samples that have a winner (== N without NaN rows)
   const uint32_t my_smem = acc_smem_u32(stage_smem) + (uint32_t)warp * WARP_BYTES + lane * 16;
-  const uint32_t my_w = acc_smem_u32(stage_smem) + (uint32_t)warp * WARP_BYTES + STAGES * SLOT_BYTES + lane * 32;
+  constexpr uint32_t W_OFF = STAGES * SLOT_BYTES;  // prototype area relative to my_smem: [VPL][2 halves][32 lanes x 16 B]
   bool act[VPL];  // FULLD: D == 128 * VPL * WPR, every slab of every lane is inside the row
 #pragma unroll
   for (int v = 0; v < VPL; ++v) act[v] = FULLD || col0 + v * 128 < D;
@@ -254,51 +251,65 @@ __global__ void __launch_bounds__(THREADS, 2) accumulate_kernel(
     const int mid = (lo + hi) >> 1;
     if (offsets[mid] <= p_begin) lo = mid; else hi = mid;
   }
-  SegCursor use{p_begin, lo, offsets[lo + 1]};  // consumer position
-  SegCursor pre = use;                          // prefetch position (runs STAGES - 1 batches ahead)
+  // prefetch side: next position, its segment and the segment's end; offset ring filled up to `filled`
+  int32_t pp = p_begin, pseg = lo, pseg_end = offsets[lo + 1];
+  bool pnew = true;  // the next batch is the first one this team takes from its segment
+  int32_t filled = p_begin;
+  const uint32_t my_win = acc_smem_u32(stage_smem) + (uint32_t)warp * WARP_BYTES + STAGES * SLOT_BYTES + VPL * 1024;
+  auto perm_at = [&](int32_t p) { return perm[p < p_end ? p : p_end - 1]; };  // positions past the range are never used
+  int32_t perm_nxt = perm_at(filled + lane);  // always one window ahead of the ring
+  const uint32_t row_bytes = (uint32_t)ldx * 4u;
+  const char* __restrict__ my_src = reinterpret_cast<const char*>(X + col0);
+  uint32_t fifo = 0;  // one byte per batch in flight, oldest lowest: rows | 0x80 if the batch starts a segment
 
-  // permutation window: lane l holds perm[win + l] (cur) and perm[win + 32 + l] (nxt)
-  int32_t win = p_begin;
-  auto perm_at = [&](int32_t p) { return perm[p < total ? p : total - 1]; };
-  int32_t perm_cur = perm_at(win + lane), perm_nxt = perm_at(win + 32 + lane);
-
-  const float* __restrict__ my_src = X + col0;
-  const uint32_t ld32 = (uint32_t)ldx;  // one 32 x 32 -> 64 bit multiply per row address
-  auto issue = [&](int stage) {  // every lane copies its own 16-byte pieces of the next batch
-    if (pre.p < p_end) {
-      const int nb = pre.next_batch(offsets, p_end, U);
-      if (pre.p + nb > win + 64) {  // slide the window (nb <= 32, so one step is enough)
-        win += 32;
-        perm_cur = perm_nxt;
-        perm_nxt = perm_at(win + 32 + lane);
+  auto issue = [&](int stage, int fifo_pos) {  // every lane copies its own 16-byte pieces of the next batch
+    if (pp < p_end) {
+      while (pp >= pseg_end) {  // skip empty segments
+        ++pseg;
+        pseg_end = offsets[pseg + 1];
+        pnew = true;
       }
+      const int32_t lim = p_end < pseg_end ? p_end : pseg_end;
+      const int nb = lim - pp < U ? lim - pp : U;
+      if (pp + U > filled) {  // next 32 positions into the ring (never over a slot that is still to be read)
+        const uint32_t slot = (uint32_t)(filled + lane) & 63u;
+        const uint64_t off = (uint64_t)(uint32_t)perm_nxt * row_bytes;
+        asm volatile("st.shared.u64 [%0], %1;" ::"r"(my_win + slot * 8), "l"(off) : "memory");
+        if (slot < 8) asm volatile("st.shared.u64 [%0], %1;" ::"r"(my_win + (slot + 64) * 8), "l"(off) : "memory");
+        filled += 32;
+        perm_nxt = perm_at(filled + lane);
+        __syncwarp();
+      }
+      const uint32_t wa = my_win + (((uint32_t)pp & 63u) << 3);
       const uint32_t dst = my_smem + (uint32_t)stage * SLOT_BYTES;
+      uint64_t off[U];  // all U slots are read (the mirror keeps them inside the ring), only nb rows are copied
+#pragma unroll
+      for (int u = 0; u < U; ++u) asm volatile("ld.shared.u64 %0, [%1];" : "=l"(off[u]) : "r"(wa + u * 8));
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int o = pre.p + u - win;  // 0 .. 63
-        const int32_t a = __shfl_sync(kFullMask, perm_cur, o & 31);
-        const int32_t b = __shfl_sync(kFullMask, perm_nxt, o & 31);
-        const float* src = my_src + (uint64_t)(uint32_t)(o < 32 ? a : b) * ld32;
         if (u < nb) {
+          const char* src = my_src + off[u];
 #pragma unroll
           for (int v = 0; v < VPL; ++v)
             if (FULLD || act[v])
               asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (u * VPL + v) * 512),
-                           "l"(src + v * 128)
+                           "l"(src + v * 512)
                            : "memory");
         }
       }
-      pre.p += nb;
+      fifo |= (uint32_t)(nb | (pnew ? 0x80 : 0)) << (8 * fifo_pos);
+      pnew = false;
+      pp += nb;
     }
     asm volatile("cp.async.commit_group;" ::: "memory");  // possibly empty: keeps the group count uniform
   };
 #pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) issue(s);
+  for (int s = 0; s < STAGES - 1; ++s) issue(s, s);
 
   double* __restrict__ Sk = part;
   double acc[VPL][4];
   double run_k = 0.0, run_d = 0.0;  // sums of the rows this lane evaluates (row slot row_of_lane)
-  int seg = -1;
+  int seg = ~lo;  // < 0: nothing accumulated yet, the first segment is ~seg
   auto load_w = [&](int sgm) {
     seg = sgm;
 #pragma unroll
@@ -307,8 +318,8 @@ __global__ void __launch_bounds__(THREADS, 2) accumulate_kernel(
       if (act[v]) {
         const double2 a = *reinterpret_cast<const double2*>(W + (int64_t)seg * D + c);
         const double2 b = *reinterpret_cast<const double2*>(W + (int64_t)seg * D + c + 2);
-        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(my_w + v * 1024), "d"(a.x), "d"(a.y) : "memory");
-        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(my_w + v * 1024 + 16), "d"(b.x), "d"(b.y) : "memory");
+        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(my_smem + W_OFF + v * 1024), "d"(a.x), "d"(a.y) : "memory");
+        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(my_smem + W_OFF + v * 1024 + 512), "d"(b.x), "d"(b.y) : "memory");
       }
       acc[v][0] = acc[v][1] = acc[v][2] = acc[v][3] = 0.0;
     }
@@ -338,13 +349,19 @@ __global__ void __launch_bounds__(THREADS, 2) accumulate_kernel(
   };
 
   int stage = 0, parity = 0;
-  while (use.p < p_end) {
-    const int nb = use.next_batch(offsets, p_end, U);
-    if (use.seg != seg) {
-      if (seg >= 0) flush();
-      load_w(use.seg);
+  while (fifo & 0x7fu) {  // batches in flight
+    const int nb = (int)(fifo & 0x7fu);
+    if (fifo & 0x80u) {  // first batch of a segment: move on to the next segment that has samples
+      int nseg = ~seg;
+      if (seg >= 0) {
+        flush();
+        nseg = seg + 1;
+        while (offsets[nseg + 1] == offsets[nseg]) ++nseg;
+      }
+      load_w(nseg);
     }
-    issue(stage == 0 ? STAGES - 1 : stage - 1);  // refill the slot consumed in the previous iteration
+    fifo >>= 8;
+    issue(stage == 0 ? STAGES - 1 : stage - 1, STAGES - 2);  // refill the slot consumed in the previous iteration
     asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 1) : "memory");
     const uint32_t rows = my_smem + (uint32_t)stage * SLOT_BYTES;
 
@@ -365,11 +382,11 @@ __global__ void __launch_bounds__(THREADS, 2) accumulate_kernel(
               asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
                            : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
                            : "r"(rows + (u * VPL + v) * 512));
-              // one conversion in four goes through the XU pipe (F2F, ~27 clk per warp instruction, otherwise
-              // idle), the rest through the ALU/FMA pipes: neither saturates
+              // one or two conversions in four go through the XU pipe (F2F, ~27 clk per warp instruction,
+              // otherwise idle), the rest through the ALU/FMA pipes: neither saturates
               xd[u][v][0] = (double)x.x;
               xd[u][v][1] = f32_as_f64(x.y);
-              xd[u][v][2] = f32_as_f64(x.z);
+              xd[u][v][2] = XU2 ? (double)x.z : f32_as_f64(x.z);
               xd[u][v][3] = f32_as_f64(x.w);
             }
           }
@@ -377,7 +394,7 @@ __global__ void __launch_bounds__(THREADS, 2) accumulate_kernel(
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             double w0, w1;
-            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(w0), "=d"(w1) : "r"(my_w + v * 1024 + h * 16));
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(w0), "=d"(w1) : "r"(my_smem + W_OFF + v * 1024 + h * 512));
 #pragma unroll
             for (int u = 0; u < U; ++u) {
               if (ALL || u < nb) {
@@ -402,8 +419,10 @@ __global__ void __launch_bounds__(THREADS, 2) accumulate_kernel(
         parity ^= 1;
       }
       // each lane evaluates the weight and the distance of its row slot (32 / U lanes per slot, redundantly)
+      // dbgsom/BaseSom.py:536 squares the distance again; d2 itself is that square to one rounding, and the
+      // exponential no longer waits for the square root
       const double my_dist = sqrt(my_d2);
-      const double my_k = 1.0 - sqrt(1.0 - exp(-inv_var * (my_dist * my_dist)));
+      const double my_k = 1.0 - sqrt(1.0 - exp(-inv_var * my_d2));
       if (ALL || row_of_lane<U>(lane) < nb) {
         run_k += my_k;
         run_d += my_dist;
@@ -426,13 +445,12 @@ __global__ void __launch_bounds__(THREADS, 2) accumulate_kernel(
       body(std::true_type{});
     else
       body(std::false_type{});
-    use.p += nb;
     if (++stage == STAGES) stage = 0;
   }
   if (seg >= 0) flush();
 }
 
-template <int VPL, int WPR, int U>
+template <int VPL, int WPR, int U, bool XU2 = false>
 int launch_accumulate(const dbgsom_accumulate_args& a, const int32_t* perm, const int32_t* offsets, cudaStream_t s) {
   // one warp per row (WPR = 1): 6 warps per CTA leave 168 registers per thread at two CTAs per SM, enough
   // for the U * VPL * 4 converted elements + prototype + sums without spilling (at 128 registers the
@@ -440,12 +458,13 @@ int launch_accumulate(const dbgsom_accumulate_args& a, const int32_t* perm, cons
   constexpr int THREADS = WPR == 1 ? 192 : 256;
   constexpr int STAGES = WPR == 1 ? 4 : 3;
   constexpr int TEAMS = THREADS / 32 / WPR;
-  const size_t smem = (size_t)(THREADS / 32) * (STAGES * U * VPL * 512 + VPL * 1024);
-  auto kern = a.D == 128 * VPL * WPR ? accumulate_kernel<VPL, WPR, U, THREADS, STAGES, true>
-                                     : accumulate_kernel<VPL, WPR, U, THREADS, STAGES, false>;
+  const size_t smem = (size_t)(THREADS / 32) * (STAGES * U * VPL * 512 + VPL * 1024 + ACC_WIN_BYTES);
+  auto kern = a.D == 128 * VPL * WPR ? accumulate_kernel<VPL, WPR, U, THREADS, STAGES, true, XU2>
+                                     : accumulate_kernel<VPL, WPR, U, THREADS, STAGES, false, XU2>;
   DBGSOM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = (int)((220 * 1024) / (smem + 2048));
-  if (per_sm > 2) per_sm = 2;  // register budget
+  int per_sm = 1;  // resident CTAs per SM: 2 by registers (__launch_bounds__) if the staging rings fit twice
+  DBGSOM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
+  if (per_sm > 2) per_sm = 2;
   if (per_sm < 1) per_sm = 1;
   int64_t blocks = 148 * per_sm;
   const int64_t useful = ceil_div<int64_t>(ceil_div<int64_t>(a.N, 4 * U), TEAMS);  // >= 4 batches per team
@@ -525,12 +544,18 @@ int run_accumulate(const dbgsom_accumulate_args& a, cudaStream_t s) {
   const int D4 = a.D;
   static const char* tune_u = getenv("DBGSOM_ACC_ROWS");  // tuning switch: rows per batch for D <= 256
   const int u_small = tune_u ? atoi(tune_u) : 0;
+  // two float -> double conversions in four on the XU pipe (default; DBGSOM_ACC_XU2=0: one in four).  With the lean
+  // loop control the kernel has XU cycles to spare: 10M x 256 rows 1.80 -> 1.72 ms, 12.5M x 128 rows 1.33 -> 1.30 ms
+  static const char* tune_xu = getenv("DBGSOM_ACC_XU2");
+  const bool xu2 = !tune_xu || atoi(tune_xu) != 0;
   if (D4 <= 128) {
     if (u_small == 4) return launch_accumulate<1, 1, 4>(a, ws.perm, ws.offsets, s);
+    if (xu2) return launch_accumulate<1, 1, 8, true>(a, ws.perm, ws.offsets, s);
     return launch_accumulate<1, 1, 8>(a, ws.perm, ws.offsets, s);
   }
   if (D4 <= 256) {
     if (u_small == 2) return launch_accumulate<2, 1, 2>(a, ws.perm, ws.offsets, s);
+    if (xu2) return launch_accumulate<2, 1, 4, true>(a, ws.perm, ws.offsets, s);
     return launch_accumulate<2, 1, 4>(a, ws.perm, ws.offsets, s);
   }
   if (D4 <= 512) return launch_accumulate<4, 1, 2>(a, ws.perm, ws.offsets, s);

@@ -13,7 +13,7 @@ _LIB = None
 LIB_NAME = "libdbgsom_b200.so"
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 SELECT_OFF, SELECT_FLAG, SELECT_REFINE = 0, 1, 2
 MAX_CAND = 8
 BMU_SIMT = 0
@@ -63,7 +63,7 @@ class BmuArgs(C.Structure):
         ("workspace_bytes", c_size_t),
         ("d_row_perm", c_void_p),
         ("d_tile_mask", c_void_p),
-        ("reserved0", c_void_p),
+        ("d_tile_bound", c_void_p),
         ("select", c_int32),
         ("select_granule", c_int32),
     ]
@@ -130,6 +130,9 @@ SIGNATURES = {
          c_void_p, c_void_p, c_void_p, c_void_p],
     ),
     "dbgsom_exclude_duplicates": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dbgsom_tile_bounds": (
+        c_int, [c_void_p, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p, c_int, c_void_p, c_void_p]
+    ),
     "dbgsom_prepare_bias": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dbgsom_bmu_workspace_bytes": (c_size_t, [c_int64, c_int32]),
     "dbgsom_bmu": (c_int, [C.POINTER(BmuArgs), c_void_p]),

@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) bmu_resolve_kernel(
     int32_t* __restrict__ idx_out, double* __restrict__ dist_out, unsigned long long* __restrict__ stats,
     // flagged-sample policy (tensor back end only; xnorm16 == nullptr disables the shortcut)
     const float* __restrict__ xnorm16, const float* __restrict__ wmax, float bound_coef, float acc_coef, float inv_scale2,
-    float tie_rel, int32_t* __restrict__ rescan_count, int32_t* __restrict__ rescan_rows) {
+    float tie_rel, int32_t* __restrict__ rescan_count, int32_t* __restrict__ rescan_rows, int gap_is_proven) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * WARPS_PER_BLOCK;
@@ -98,7 +98,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) bmu_resolve_kernel(
           const int jb = idx_out[row];
           const double db = sqdist_f64(x, W + (int64_t)jb * D, D, lane);
           const double bound = (double)(tensor_score_bound(xnorm16[row], wmax, bound_coef, acc_coef) * inv_scale2);
-          const double gap = (double)(__int_as_float(cand_idx[row * kMaxCand]) * inv_scale2) + 2.0 * bound;
+          // (with per-tile bounds -- bmu_tc.cu, TB -- the slot already holds "second smallest upper bound minus
+          // smallest lower bound" of the exact scores, a proven bound on the gap by itself)
+          const double gap = (double)(__int_as_float(cand_idx[row * kMaxCand]) * inv_scale2) + (gap_is_proven ? 0.0 : 2.0 * bound);
           if (jb >= 0 && gap <= (double)tie_rel * (db - 2.0 * bound)) {
             top.offer(db, jb);
             full = false;
@@ -271,13 +273,13 @@ int launch_bmu_resolve(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStr
   if (a.n_bmu == 1) {
     bmu_resolve_kernel<1><<<(unsigned)blocks, WARPS_PER_BLOCK * 32, 0, s>>>(
         a.d_X, a.N, a.D, a.ldx, a.d_W, a.M, ws.cand_idx, ws.cand_count, a.want_dist, a.d_idx, a.d_dist, stats, xn,
-        a.d_wmax, coef, acc_coef, inv_s2, tie, ws.rescan_count, ws.rescan_rows);
+        a.d_wmax, coef, acc_coef, inv_s2, tie, ws.rescan_count, ws.rescan_rows, tile_bounds_active(a) ? 1 : 0);
     DBGSOM_LAUNCH_CHECK();
     return wide ? launch_rescan<1, 8, float>(a, ws, s) : launch_rescan<1, 8, double>(a, ws, s);
   }
   bmu_resolve_kernel<2><<<(unsigned)blocks, WARPS_PER_BLOCK * 32, 0, s>>>(
       a.d_X, a.N, a.D, a.ldx, a.d_W, a.M, ws.cand_idx, ws.cand_count, a.want_dist, a.d_idx, a.d_dist, stats, xn,
-      a.d_wmax, coef, acc_coef, inv_s2, tie, ws.rescan_count, ws.rescan_rows);
+      a.d_wmax, coef, acc_coef, inv_s2, tie, ws.rescan_count, ws.rescan_rows, 0);
   DBGSOM_LAUNCH_CHECK();
   return wide ? launch_rescan<2, 8, float>(a, ws, s) : launch_rescan<2, 8, double>(a, ws, s);
 }

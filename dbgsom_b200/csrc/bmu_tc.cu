@@ -386,7 +386,19 @@ struct Barriers {
 // 2 = REFINE pass (the classic three-pass search over exactly those column tiles).  Both need the CTA-pair form with
 // the sample tile in tensor memory.  row_perm: the shadows are in sorted sample order (shadow row p = sample
 // row_perm[p]); every per-sample read and write below goes through it.
-template <int NPASS, int NB, int BN, int RES_KB, int AKB, int CL, bool PAIR = false, int SEL = 0>
+// TB: per-tile error bounds (streamed forms, one winner).  tile_bound[2 q], [2 q + 1] = max ||u_j|| and max |wnorm_j|
+// over shadow columns [128 q, 128 q + 128) (dbgsom_tile_bounds).  The rounding error of a score is proportional to the
+// norm of ITS prototype, so a column of tile T is off by at most B_T = bound(||x'||, maxima of T) instead of the bound
+// taken with the maxima of the whole map.  On large half-trained maps most prototypes form a flat sheet of small norm
+// far from the samples while a few unfolded ones carry the maxima: thousands of sheet prototypes fell inside the
+// global bound of a row and none of these rows could be proven a near-tie (2 B / d^2 ~ 1.1e-6 at the config-5 shape:
+// 6 % of the rows went to the float64 re-scan of all prototypes, 3x the time of the search itself).  With tile bounds
+// the tables work in KEY units, key = score - B_T (a lower bound of the exact score): a column is a candidate iff its
+// key <= U, the smallest upper bound (score + B_T) seen so far, and a flagged row carries U2 - min key -- a proven
+// bound on the exact best / second-best gap -- instead of the raw score gap.  Tile maxima are floored at 1/8 of the
+// global ones: the coefficients were calibrated against global maxima (common.cuh), the floor keeps a margin.
+constexpr float kTileBoundFloor = 0.125f;
+template <int NPASS, int NB, int BN, int RES_KB, int AKB, int CL, bool PAIR = false, int SEL = 0, bool TB = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     bmu_cand_tensor_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                            const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
@@ -398,7 +410,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                            int32_t* __restrict__ idx_out, int32_t* __restrict__ cand_idx,
                            uint8_t* __restrict__ cand_count, const int32_t* __restrict__ row_perm,
                            unsigned long long* __restrict__ tile_mask,
-                           int fg_shift, unsigned long long* __restrict__ sel_stats) {
+                           int fg_shift, unsigned long long* __restrict__ sel_stats,
+                           const float* __restrict__ tile_bound) {
+  static_assert(!TB || (NB == 1 && SEL == 0 && BN % 128 == 0), "tile bounds: classic one-winner search, 128-column granules");
   using C = Cfg<NPASS, BN, RES_KB, AKB, PAIR && AKB == 0 && RES_KB == 0, SEL == 1 ? kFlagChunkBytes : 0>;
   static_assert(SEL == 0 || (PAIR && AKB > 0 && NB == 1 && NPASS == (SEL == 1 ? 1 : 3)),
                 "selective search: CTA pairs, sample tile in tensor memory, one winner");
@@ -905,6 +919,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const int64_t row = tile_of(it) * BM + t;
       const int64_t orow = orow_n1 >= 0 ? orow_n1 : 0;
       const float tau = row < N ? 2.f * tensor_score_bound(xn_n1, wmax, bound_coef, acc_coef) : 0.f;
+      const float xn_row = row < N ? xn_n1 : 0.f;
       unsigned long long selm = mask_n1;
       orow_n1 = orow_n2;
       xn_n1 = orow_n1 >= 0 ? xnorm16[orow_n1] : 0.f;  // address known since the previous iteration
@@ -920,6 +935,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         if (SEL == 2) {
           nt = __ffsll((long long)selm) - 1;
           selm &= selm - 1;
+        }
+        float kb = 0.f;  // TB: the bound of this column tile for my row (keys = score - kb); 0 otherwise
+        if (TB) {
+          const float* tb = tile_bound + 2 * (nt * (BN / 128));
+          float um = tb[0], wm = tb[1];
+#pragma unroll
+          for (int q = 1; q < BN / 128; ++q) {
+            um = fmaxf(um, tb[2 * q]);
+            wm = fmaxf(wm, tb[2 * q + 1]);
+          }
+          um = fmaxf(um, kTileBoundFloor * wmax[0]);
+          wm = fmaxf(wm, kTileBoundFloor * wmax[2]);
+          const float xw = xn_row * um;
+          kb = xw * bound_coef + acc_coef * (xw + wm);
         }
         mbar_wait(&bars->tmem_full[acc], acc_phase);
         tc_fence_after();
@@ -989,7 +1018,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           // fold into the running minima; NB == 1 also shares the minimum with the other three
           // warps of this row (a racy read-modify-write is fine: every value written is a score that
           // was really seen, so the threshold can only be looser than necessary, never tighter)
-          if (NB == 1) {
+          if (TB) {
+            // upper bounds: v of this chunk's best column; m1 / m2 = the two smallest of MY chunks (distinct columns, so
+            // the merge below can form the second smallest upper bound of the row); the row shares its smallest one
+            const float v = a1 + kb;
+            const float sh = row_min[t];
+            if (v < sh) row_min[t] = v;
+            m2 = fminf(m2, fmaxf(m1, v));
+            m1 = fminf(m1, v);
+            thr = fminf(m1, sh) + kb;  // in score units for this tile: key <= U
+          } else if (NB == 1) {
             const float sh = row_min[t];
             if (a1 < sh) row_min[t] = a1;
             m1 = fminf(m1, fminf(a1, sh));
@@ -1009,8 +1047,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           //  * several: the scores are parked in local memory so that a loop can index them, lanes advancing
           //    through their own in-bound scores in parallel.
           if (a1 <= thr) {
-            if (a1 >= gate) {
-              evicted = fminf(evicted, a1);
+            if (a1 - kb >= gate) {
+              evicted = fminf(evicted, a1 - kb);
             } else {
               uint32_t inb = 0;
 #pragma unroll
@@ -1024,7 +1062,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
               }
               if ((inb & (inb - 1)) == 0) {
                 if (inb) {
-                  const float2 o = slow_offer(a1, col + __ffs(inb) - 1, my_val_addr, epi_const_addr);
+                  const float2 o = slow_offer(a1 - kb, col + __ffs(inb) - 1, my_val_addr, epi_const_addr);
                   gate = o.x;
                   evicted = fminf(evicted, o.y);
                 }
@@ -1041,8 +1079,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                   for (int e = 0; e < 4; ++e) {
                     // in bound but not below the gate as it stands (it only falls): evicted, branch-free
                     const float se = sc[4 * g + e];
-                    const bool in = se <= thr, out = se >= gate;
-                    evicted = fminf(evicted, in && out ? se : __int_as_float(0x7f800000));
+                    const bool in = se <= thr, out = se - kb >= gate;
+                    evicted = fminf(evicted, in && out ? se - kb : __int_as_float(0x7f800000));
                     need |= (in && !out ? 1u : 0u) << (4 * g + e);
                   }
                 }
@@ -1050,7 +1088,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 while (need) {
                   const int e = __ffs(need) - 1;
                   need &= need - 1;
-                  const float se = sc[e];
+                  const float se = sc[e] - kb;
                   if (se >= gate) {
                     evicted = fminf(evicted, se);
                   } else {
@@ -1083,12 +1121,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
         for (int q = 0; q < EPI_SUBS; ++q) {
           const float4 st = sub_state[t * EPI_SUBS + q];
-          if (NB == 2) g2 = fminf(fmaxf(g1, st.x), fminf(g2, st.y));
+          if (NB == 2 || TB) g2 = fminf(fmaxf(g1, st.x), fminf(g2, st.y));
           g1 = fminf(g1, st.x);
           ev = fminf(ev, st.z);
         }
         const float gm = NB == 1 ? g1 : g2;
-        const float gthr = gm < 1.0e38f ? gm + tau : kInf;
+        // TB: the tables hold keys (score - tile bound) and g1 is the smallest upper bound: in bound iff key <= g1
+        const float gthr = gm < 1.0e38f ? (TB ? gm : gm + tau) : kInf;
         // the sixteen (score, prototype) pairs of the row: independent loads first, then branch-free bookkeeping
         float v[EPI_SUBS * KSUB];
         int jx[EPI_SUBS * KSUB];
@@ -1119,7 +1158,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           // two smallest approximate scores instead (>= 0, float bits), which tightens the near-tie test of the re-score
           int32_t* slots = cand_idx + orow * kMaxCand;
           if (overflow) {
-            slots[0] = __float_as_int(fmaxf(sv - bv, 0.f));
+            // TB: second smallest upper bound minus smallest lower bound = a proven bound on the exact gap
+            slots[0] = __float_as_int(fmaxf((TB ? (g2 < 1.0e38f ? g2 : __int_as_float(0x7f800000)) : sv) - bv, 0.f));
           } else if (cnt == 1) {
             slots[0] = best;
           } else {
@@ -1196,7 +1236,7 @@ int sm_count() {
   return n;
 }
 
-template <int NPASS, int NB, int BN, int RES_KB, int AKB, int CL, bool PAIR = false, int SEL = 0>
+template <int NPASS, int NB, int BN, int RES_KB, int AKB, int CL, bool PAIR = false, int SEL = 0, bool TB = false>
 int launch_cfg_cl(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t s) {
   using C = Cfg<NPASS, BN, RES_KB, AKB, PAIR && AKB == 0 && RES_KB == 0, SEL == 1 ? kFlagChunkBytes : 0>;
   CUtensorMap mxh, mxl, mwh, mwl;
@@ -1228,7 +1268,7 @@ int launch_cfg_cl(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t
       fprintf(stderr, "dbgsom: K1 takes wnorm through the bias k-step, E = %g\n", e);
     }
   }
-  auto kern = bmu_cand_tensor_kernel<NPASS, NB, BN, RES_KB, AKB, CL, PAIR, SEL>;
+  auto kern = bmu_cand_tensor_kernel<NPASS, NB, BN, RES_KB, AKB, CL, PAIR, SEL, TB>;
   DBGSOM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   const int KB = (int)(a.ld16 / BK);
   const int NT = a.Mpad / BN;  // prototypes are permuted over all Mpad shadow rows
@@ -1268,7 +1308,8 @@ int launch_cfg_cl(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t
                                      a.n_bmu == 1 ? a.ties_any : 0, a.d_xnorm16, a.d_wmax, coef, acc_coef, a.d_idx, ws.cand_idx, ws.cand_count,
                                      a.d_row_perm, reinterpret_cast<unsigned long long*>(a.d_tile_mask),
                                      a.select_granule == 64 ? 6 : 7,
-                                     a.d_stats ? reinterpret_cast<unsigned long long*>(a.d_stats) + 4 : (unsigned long long*)nullptr));
+                                     a.d_stats ? reinterpret_cast<unsigned long long*>(a.d_stats) + 4 : (unsigned long long*)nullptr,
+                                     TB ? a.d_tile_bound : (const float*)nullptr));
   DBGSOM_LAUNCH_CHECK();
   return DBGSOM_OK;
 }
@@ -1315,6 +1356,12 @@ bool streamed_segmented(const dbgsom_bmu_args& a) {
   static const bool segm = getenv("DBGSOM_TC_SEGM") == nullptr || atoi(getenv("DBGSOM_TC_SEGM")) != 0;
   return segm && streamed_pairs(a);
 }
+}  // namespace
+// per-tile error bounds (template flag TB): the streamed pair forms, one winner, the caller supplied the tile maxima
+bool tile_bounds_active(const dbgsom_bmu_args& a) {
+  return a.d_tile_bound != nullptr && a.n_bmu == 1 && a.select == DBGSOM_SELECT_OFF && streamed_pairs(a);
+}
+namespace {
 
 template <int NPASS, int NB>
 int launch_shape(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t s) {
@@ -1335,6 +1382,12 @@ int launch_shape(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t 
     if (streamed_pairs(a)) {
       // segmented accumulation (128-column tiles, partial accumulators summed in the epilogue) keeps the error bound
       // of D = 256 at any D; DBGSOM_TC_SEGM=0 selects the one-chain form with 256-column tiles
+      if constexpr (NB == 1) {
+        if (tile_bounds_active(a)) {
+          if (streamed_segmented(a)) return launch_cfg_cl<NPASS, NB, 128, 0, 0, 2, true, 0, true>(a, ws, s);
+          return launch_cfg_cl<NPASS, NB, 256, 0, 0, 2, true, 0, true>(a, ws, s);
+        }
+      }
       if (streamed_segmented(a)) return launch_cfg_cl<NPASS, NB, 128, 0, 0, 2, true>(a, ws, s);
       return launch_cfg_cl<NPASS, NB, 256, 0, 0, 2, true>(a, ws, s);
     }

@@ -10,6 +10,7 @@ bool bmu_select_supported(int64_t N, int64_t ld16, int Mpad, int n_bmu, int gran
 int run_prepare_w(const double*, int, int, const float*, float, float*, uint16_t*, uint16_t*, int64_t, int,
                   const int32_t*, float*, double*, float*, cudaStream_t);
 int run_exclude_duplicates(const double*, int, int, const int32_t*, float*, unsigned long long*, cudaStream_t);
+int run_tile_bounds(const double*, int, int, const double*, float, const int32_t*, const float*, int, float*, cudaStream_t);
 int run_prepare_bias(const float*, int, const float*, uint16_t*, float*, cudaStream_t);
 int run_row_ops(double*, int, const int32_t*, int, cudaStream_t);
 int run_gather_rows(const float*, int64_t, int, const int64_t*, int, double*, cudaStream_t);
@@ -124,6 +125,13 @@ int dbgsom_exclude_duplicates(const double* d_W, int M, int D, const int32_t* d_
   if (!d_W || !d_wnorm || !d_hash || M <= 0 || D <= 0) return DBGSOM_E_BADARG;
   return run_exclude_duplicates(d_W, M, D, d_col_of_proto, d_wnorm, reinterpret_cast<unsigned long long*>(d_hash),
                                 as_stream(stream));
+}
+
+int dbgsom_tile_bounds(const double* d_W, int M, int D, const double* d_wshift, float scale,
+                       const int32_t* d_proto_of_col, const float* d_wnorm, int Mpad, float* d_tile_bound, void* stream) {
+  if (!d_W || !d_wshift || !d_wnorm || !d_tile_bound || M <= 0 || D <= 0 || Mpad < M) return DBGSOM_E_BADARG;
+  if (Mpad % 128 != 0) return DBGSOM_E_UNSUPPORTED;
+  return run_tile_bounds(d_W, M, D, d_wshift, scale, d_proto_of_col, d_wnorm, Mpad, d_tile_bound, as_stream(stream));
 }
 
 int dbgsom_prepare_bias(const float* d_wnorm, int Mpad, const float* d_wmax, uint16_t* d_Wb16, float* d_bias_scale,

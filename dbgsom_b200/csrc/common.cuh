@@ -231,6 +231,9 @@ inline float tensor_acc_coef(int n_pass, int64_t ld16, int strict) {
 }
 // accumulation coefficient of the kernel form that runs for these arguments (bmu_tc.cu)
 float tensor_acc_coef_args(const dbgsom_bmu_args& a);
+// true if the candidate search runs with per-tile error bounds for these arguments (bmu_tc.cu): a flagged row's first
+// candidate slot then holds a proven bound on the exact best / second-best gap instead of the raw score gap
+bool tile_bounds_active(const dbgsom_bmu_args& a);
 __host__ __device__ inline float tensor_bound_coef(int n_pass, float bound_scale) {
   if (n_pass == 1) return (bound_scale > 0.f ? bound_scale : 0.25f) * 1.953125e-3f;
   return (bound_scale > 0.f ? bound_scale : 0.0625f) * 1.9073486e-6f;

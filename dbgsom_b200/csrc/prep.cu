@@ -171,6 +171,48 @@ __global__ void __launch_bounds__(128) prepare_w_kernel(const double* __restrict
   }
 }
 
+// ------------------------------------------------------------------------------------------ tile bounds
+// Per 128 shadow columns: max ||u_j|| and max |wnorm_j| over the prototypes stored there (padding columns and
+// prototypes taken out of the search -- wnorm = +inf -- do not count).  One CTA per tile, a warp per column; the
+// maxima are rounded up so that they stay upper bounds.  Feeds the per-tile error bounds of the candidate search
+// (bmu_tc.cu, TB).
+__global__ void __launch_bounds__(256) tile_bounds_kernel(const double* __restrict__ W, int M, int D,
+                                                         const double* __restrict__ wshift, float scale,
+                                                         const int32_t* __restrict__ proto_of_col,
+                                                         const float* __restrict__ wnorm, float* __restrict__ out) {
+  __shared__ float red[2][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float um = 0.f, wm = 0.f;
+  for (int i = warp; i < 128; i += 8) {
+    const int c = blockIdx.x * 128 + i;
+    const int j = proto_of_col ? proto_of_col[c] : c;
+    const float wn = wnorm[c];
+    if (j < 0 || j >= M || !(fabsf(wn) < 3.0e38f)) continue;  // warp-uniform
+    double nu = 0.0;
+    for (int d = lane; d < D; d += 32) {
+      const double u = (W[(int64_t)j * D + d] - wshift[d]) * (double)scale;
+      nu = fma(u, u, nu);
+    }
+    nu = warp_sum(nu);
+    um = fmaxf(um, __double2float_ru(sqrt(nu)));
+    wm = fmaxf(wm, fabsf(wn));
+  }
+  if (lane == 0) {
+    red[0][warp] = um;
+    red[1][warp] = wm;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 1; q < 8; ++q) {
+      um = fmaxf(um, red[0][q]);
+      wm = fmaxf(wm, red[1][q]);
+    }
+    out[2 * blockIdx.x] = um;
+    out[2 * blockIdx.x + 1] = wm;
+  }
+}
+
 // ------------------------------------------------------------------------------------------ duplicates
 // Exact copies among the prototypes.  The reference breaks exact distance ties by the lowest index
 // (sklearn/utils/_heap.pyx:46), so a prototype that equals a LOWER-indexed one element by element can never be
@@ -330,6 +372,13 @@ int run_prepare_w(const double* W, int M, int D, const float* shift, float scale
   prepare_w_kernel<<<rows, 128, 0, s>>>(W, M, D, shift, wshift, scale, W32, reinterpret_cast<__half*>(W16_hi),
                                         reinterpret_cast<__half*>(W16_lo), ld16, W16_hi ? col_of_proto : nullptr, wnorm,
                                         wmax);
+  DBGSOM_LAUNCH_CHECK();
+  return DBGSOM_OK;
+}
+
+int run_tile_bounds(const double* W, int M, int D, const double* wshift, float scale, const int32_t* proto_of_col,
+                    const float* wnorm, int Mpad, float* out, cudaStream_t s) {
+  tile_bounds_kernel<<<Mpad / 128, 256, 0, s>>>(W, M, D, wshift, scale, proto_of_col, wnorm, out);
   DBGSOM_LAUNCH_CHECK();
   return DBGSOM_OK;
 }

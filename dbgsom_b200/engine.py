@@ -153,6 +153,12 @@ class DeviceEngine:
         # from the permutation K2 leaves behind) and the shadow columns in map-patch order.  DBGSOM_SELECT=0 turns it off.
         self.select_enabled = os.environ.get("DBGSOM_SELECT", "1") != "0"
         self.select_granule = int(os.environ.get("DBGSOM_SELECT_GRANULE", "64"))
+        # Per-tile error bounds for the streamed search (D > 256, one winner; csrc/bmu_tc.cu, TB): the rounding bound of a
+        # score follows the norms of the prototypes of ITS column tile, which are coherent when the shadow columns are
+        # laid out in map patches.  DBGSOM_TILE_BOUND=0 turns it off (map-wide maxima everywhere, scattered columns).
+        self.tile_bounds_enabled = os.environ.get("DBGSOM_TILE_BOUND", "1") != "0"
+        self.tile_bound = None
+        self._tile_ready = False
         self.resort_every = int(os.environ.get("DBGSOM_RESORT_EVERY", "8"))
         self.row_perm = None      # int32 [N]: shadow row p holds sample row_perm[p] (None = natural order)
         self.tile_mask = None
@@ -228,7 +234,7 @@ class DeviceEngine:
         self._ws.clear()
         self._perm_cache.clear()
         for name in ("X", "X16_hi", "X16_lo", "xnorm16", "W", "W32", "W16_hi", "W16_lo", "Wb16", "_row_hash", "labels",
-                     "part", "hop", "_final_idx", "row_perm", "tile_mask"):
+                     "part", "hop", "_final_idx", "row_perm", "tile_mask", "tile_bound"):
             if hasattr(self, name):
                 setattr(self, name, None)
 
@@ -504,6 +510,11 @@ class DeviceEngine:
     def _prepare_w(self, W, m: int, tensor: bool, need_lo: bool, top1: bool = True, map_order: bool = False) -> int:
         torch = self.torch
         mpad = _round_up(m, 256)
+        # streamed three-pass search for one winner: per-tile bounds, columns in map patches when a topology is known
+        tile = bool(tensor and need_lo and top1 and self.tile_bounds_enabled and self.ld16 > 256)
+        if tile and self._map_order is not None and len(self._map_order) == m:
+            map_order = True
+        self._tile_ready = False
         if tensor:
             self.proto_of_col, self.col_of_proto, self.proto_stride = self._column_order(m, mpad, map_order)
             if self.W16_hi is None or self.W16_hi.shape[0] < mpad or (need_lo and self.W16_lo is None):
@@ -540,6 +551,17 @@ class DeviceEngine:
                 "dbgsom_exclude_duplicates",
             )
             self.launches += 2
+        if tile:
+            if self.tile_bound is None or self.tile_bound.numel() < mpad // 64:
+                self.tile_bound = torch.zeros(_round_up(max(mpad, self.cap), 256) // 64, dtype=torch.float32, device=self.dev)
+            nat.check(
+                self.lib.dbgsom_tile_bounds(W.data_ptr(), m, self.ldx, self.wshift.data_ptr(), self.scale,
+                                            self.proto_of_col.data_ptr(), self.wnorm.data_ptr(), mpad,
+                                            self.tile_bound.data_ptr(), self._stream()),
+                "dbgsom_tile_bounds",
+            )
+            self.launches += 1
+            self._tile_ready = True
         # experiment, off by default: wnorm enters the accumulator through an extra k-step (dbgsom_prepare_bias).  It
         # halves the epilogue's shared-memory loads but measured no gain (D = 256: MMA bound; D = 128: the epilogue is
         # bound by its instruction count, not by the shared-memory pipe) -- see DESIGN.md, K1.
@@ -601,6 +623,8 @@ class DeviceEngine:
             a.d_proto_of_col = self.proto_of_col.data_ptr()
             a.proto_stride = self.proto_stride
             a.ties_any = int(self._ties_any and n_bmu == 1)
+            if self._tile_ready and n_bmu == 1 and n_pass == 3 and not selective:
+                a.d_tile_bound = self.tile_bound.data_ptr()
         a.d_W, a.d_W32, a.d_wmax = W.data_ptr(), self.W32.data_ptr(), self.wmax.data_ptr()
         a.scale, a.M, a.Mpad, a.n_bmu = self.scale, m, mpad, n_bmu
         a.backend, a.n_pass, a.bound_scale, a.tie_rel = be, n_pass, self.bound_scale, 0.0

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define DBGSOM_ABI_VERSION 7
+#define DBGSOM_ABI_VERSION 8
 
 #define DBGSOM_OK 0
 #define DBGSOM_E_BADARG (-1)      /* null pointer, non-positive size, bad enum             */
@@ -118,6 +118,16 @@ int dbgsom_prepare_w(const double* d_W, int M, int D, const float* d_shift, floa
  * d_hash: scratch, M 64-bit words. */
 int dbgsom_exclude_duplicates(const double* d_W, int M, int D, const int32_t* d_col_of_proto /*[M..] or NULL*/,
                               float* d_wnorm, uint64_t* d_hash, void* stream);
+
+/* Optional, after dbgsom_prepare_w (and dbgsom_exclude_duplicates): d_tile_bound[2 q], [2 q + 1] = max ||u_j||_2 and
+ * max |wnorm_j| over the prototypes in shadow columns [128 q, 128 q + 128), rounded up; padding columns and prototypes
+ * taken out of the search (wnorm = +inf) do not count.  d_proto_of_col as in dbgsom_bmu_args (NULL = identity),
+ * d_wshift and scale as written / given to dbgsom_prepare_w; Mpad a multiple of 128.  Passed on in
+ * dbgsom_bmu_args.d_tile_bound it lets the candidate search for D > 256 bound the rounding error of a score by the
+ * norms of its own column tile. */
+int dbgsom_tile_bounds(const double* d_W, int M, int D, const double* d_wshift /*[D]*/, float scale,
+                       const int32_t* d_proto_of_col /*[Mpad] or NULL*/, const float* d_wnorm /*[Mpad]*/, int Mpad,
+                       float* d_tile_bound /*[Mpad / 128, 2]*/, void* stream);
 
 /* Optional, after dbgsom_prepare_w (and dbgsom_exclude_duplicates): wnorm as an MMA operand.  Writes three fp16
  * pieces of -wnorm / (2 E) into the first three columns of d_Wb16[c, 0:64] (c = shadow row; the other columns must
@@ -211,7 +221,10 @@ typedef struct dbgsom_bmu_args {
    * out in map patches a row-tile pair touches few column tiles. */
   const int32_t* d_row_perm;      /* [N] or NULL */
   uint64_t* d_tile_mask;          /* [ceil(ceil(N / 128) / 2)] */
-  const void* reserved0;          /* must be NULL */
+  const float* d_tile_bound;      /* optional, [Mpad / 128, 2] from dbgsom_tile_bounds: max ||u_j|| and max |wnorm_j| per 128
+                                     shadow columns.  The candidate search for D > 256 (n_bmu = 1) then bounds the rounding
+                                     error of a score with the maxima of ITS column tile (floored at 1/8 of the map-wide
+                                     ones) instead of the map-wide maxima; NULL = map-wide bound everywhere */
   int32_t select;                 /* DBGSOM_SELECT_OFF / _FLAG / _REFINE */
   int32_t select_granule;         /* 64 or 128 prototypes per mask bit; Mpad / granule <= 64 */
 } dbgsom_bmu_args;

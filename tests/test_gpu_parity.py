@@ -682,6 +682,43 @@ def test_config2_fit_follows_the_reference_trajectory(path, backend):
     assert est.score(X[:5000], y[:5000]) >= 0.0  # the sparse-coding inference path runs at this shape
 
 
+def test_tile_bounds_are_the_column_tile_maxima():
+    """dbgsom_tile_bounds: max ||u_j|| and max |wnorm_j| per 128 shadow columns, in the column order of the search,
+    without padding columns and without prototypes taken out of the search (wnorm = +inf)."""
+    import torch
+
+    rng = np.random.default_rng(5)
+    m, d = 700, 320
+    X = rng.normal(size=(4000, d)).astype(np.float32)
+    from dbgsom_b200.topology import MapTopology
+
+    eng = engine(bmu_backend="tensor")
+    eng.load_data(X, None, 0)
+    W0 = rng.normal(size=(m, d)) * np.linspace(0.1, 3.0, m)[:, None]
+    W0[13] = W0[7]  # an exact copy: leaves a top-1 search
+    eng.set_map(W0)
+    eng.set_hops_from_topology(MapTopology.full_grid(28, 25))
+    W = eng.W[eng.cur]
+    mpad = eng._prepare_w(W, m, True, True, top1=True)
+    assert eng._tile_ready and mpad == 768
+    torch.cuda.synchronize()
+    tb = eng.tile_bound[: mpad // 64].cpu().numpy().reshape(-1, 2)
+    poc = eng.proto_of_col[:mpad].cpu().numpy()
+    wn = eng.wnorm[:mpad].cpu().numpy()
+    Wd = W[:m, :d].cpu().numpy()
+    u = (Wd - Wd.mean(axis=0)) * eng.scale
+    un = np.sqrt((u * u).sum(axis=1))
+    for t in range(mpad // 128):
+        cols = np.arange(128 * t, 128 * t + 128)
+        ok = (poc[cols] < m) & np.isfinite(wn[cols])
+        assert not ok[poc[cols] == 13].any()  # the copy does not count
+        exp_u = un[poc[cols][ok]].max() if ok.any() else 0.0
+        exp_w = np.abs(wn[cols][ok]).max() if ok.any() else 0.0
+        assert tb[t, 0] == pytest.approx(exp_u, rel=1e-6) and tb[t, 0] >= exp_u * (1 - 1e-7)
+        assert tb[t, 1] == pytest.approx(exp_w, rel=1e-6)
+    eng.close()
+
+
 @pytest.mark.parametrize("env,shape", [
     ({"DBGSOM_TC_PAIR": "0"}, ("60000", "256", "1024", "4")),
     ({"DBGSOM_TC_PAIR": "0", "DBGSOM_TC_CLUSTER": "1"}, ("60000", "256", "1024", "4")),
@@ -693,8 +730,15 @@ def test_config2_fit_follows_the_reference_trajectory(path, backend):
     # 768 accumulation steps per score at D = 4096: wrong winners with exact relative gaps up to 8e-6 with the bound of
     # D = 256; now the chain is cut into partial accumulators (segmented form), or the bound follows the chain
     ({}, ("150000", "4096", "1024", "1")),
+    # per-tile error bounds of the streamed forms (default on): the same search with the map-wide bound, and a large
+    # half-trained map -- a flat sheet of small-norm prototypes far from the samples plus a few unfolded ones -- where
+    # thousands of prototypes tie to 1e-8 and the tile bounds decide which rows can be proven near-ties
+    ({"DBGSOM_TILE_BOUND": "0"}, ("60000", "512", "1024", "3")),
+    ({}, ("40000", "2048", "4096", "6")),
+    ({"DBGSOM_TC_SEGM": "0"}, ("40000", "2048", "4096", "6")),
 ], ids=["multicast-cluster", "single-cta", "cta-pair", "cta-pair-bias-kstep", "cta-pair-streamed-segmented",
-        "cta-pair-streamed-one-chain", "multicast-streamed", "long-accumulation-chain"])
+        "cta-pair-streamed-one-chain", "multicast-streamed", "long-accumulation-chain", "streamed-map-wide-bound",
+        "tile-bounds-flat-sheet-segmented", "tile-bounds-flat-sheet-one-chain"])
 def test_tensor_kernel_variants_agree_with_simt(env, shape):
     """The forms of the tcgen05 candidate kernel (CTA pairs with cta_group::2 -- the default; sample tile in tensor
     memory for D <= 256, both operands streamed beyond; optionally wnorm as a bias k-step --, clusters with TMA

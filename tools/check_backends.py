@@ -13,9 +13,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import torch  # noqa: E402
 
-from bench import grid_hops, make_shard, sigma_at  # noqa: E402
+from bench import make_shard, sigma_at  # noqa: E402
 from dbgsom_b200 import _native as nat  # noqa: E402
 from dbgsom_b200.engine import DeviceEngine  # noqa: E402
+from dbgsom_b200.topology import MapTopology  # noqa: E402
 
 
 def main():
@@ -29,7 +30,8 @@ def main():
     eng = DeviceEngine(device="cuda:0", bmu_backend="tensor")
     eng.load_device_data(X)
     eng.init_map_from_rows(np.random.default_rng(0).choice(rows, m, replace=False), capacity=m)
-    eng.set_hops(grid_hops(side))
+    # with a topology the streamed search (D > 256) lays its shadow columns out in map patches (per-tile bounds)
+    eng.set_hops_from_topology(MapTopology.full_grid(side, side))
     total_bad = 0
     for e in range(epochs):
         W = eng.W[eng.cur]

@@ -310,6 +310,7 @@ class BaseSom(BaseEstimator):
                 if ops:
                     engine.apply_row_ops(ops, n_rows=len(topo))
                     self._hops_dirty = True
+                    self._max_map_size = max(getattr(self, "_max_map_size", 0), len(topo))  # before dead-neuron removal
                 self._host_growth_s += time.perf_counter() - tg
 
     # ------------------------------------------------------------------ after the loop

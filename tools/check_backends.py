@@ -42,7 +42,9 @@ def main():
         eng.strict_ties = True
         eng._run_bmu(eng.X, rows, eng.ldx, None, W, m, 1, False, ref, None, backend=(nat.BMU_SIMT, 0))
         eng.strict_ties = False
-        eng._run_bmu(eng.X, rows, eng.ldx, x16, W, m, 1, False, got, None, backend=(nat.BMU_TENSOR, 3))
+        # (with a topology the engine may keep the shadows sorted by winner for its selective search: pass the order on)
+        eng._run_bmu(eng.X, rows, eng.ldx, x16, W, m, 1, False, got, None, backend=(nat.BMU_TENSOR, 3),
+                     row_perm=eng.row_perm)
         diff = torch.nonzero(got[:, 0] != ref[:, 0])[:, 0]
         bad = 0
         if diff.numel():

@@ -3,7 +3,7 @@ at reduced rows or sharded over the GPUs of a box.
 
     python tools/fit_config5.py [--n 100000] [--d 4096] [--n-iter 200] [--max-neurons 16384] [--spreading-factor 0.999]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29741 \
-        tools/fit_config5.py --distributed --n 625000 --manifold --aligned        # --n = rows PER RANK
+        tools/fit_config5.py --distributed --rows 625000 --manifold --aligned     # rows PER RANK (torchrun claims --n)
 
 A large spreading factor makes the growing threshold small, so every boundary neuron grows in every coarse
 epoch and the map reaches max_neurons well inside the coarse phase.  Prints the wall time of the whole `fit`
@@ -22,7 +22,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=100_000)
+    ap.add_argument("--n", "--rows", dest="n", type=int, default=100_000, help="rows (per rank with --distributed)")
     ap.add_argument("--d", type=int, default=4096)
     ap.add_argument("--k", type=int, default=64)
     ap.add_argument("--n-iter", type=int, default=200)

@@ -179,6 +179,23 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- CTA pair (cta_group::2): one MMA stream for two SMs.  The leader CTA (cluster rank 0) issues every
 // tcgen05.mma / tcgen05.cp / tcgen05.commit for both; each CTA keeps its own sample rows in its own tensor
@@ -398,7 +415,14 @@ struct Barriers {
 // bound on the exact best / second-best gap -- instead of the raw score gap.  Tile maxima are floored at 1/8 of the
 // global ones: the coefficients were calibrated against global maxima (common.cuh), the floor keeps a margin.
 constexpr float kTileBoundFloor = 0.125f;
-template <int NPASS, int NB, int BN, int RES_KB, int AKB, int CL, bool PAIR = false, int SEL = 0, bool TB = false>
+// SGT > 0: segmented accumulation for the streamed pair form with 256-column MMAs, SGT k-blocks per chain.  An epilogue
+// thread cannot hold the 64 running sums of a 256-column tile (96 registers at 640 threads), so the sums live in TENSOR
+// memory: the two 256-column regions alternate as sum and partial accumulator -- the first chain of a tile accumulates
+// into the sum region, every later chain into the other one, and the epilogue adds each partial into the sum with
+// tcgen05.ld / tcgen05.st before handing the region back.  The regions swap roles per tile, so the final epilogue of
+// a tile overlaps the first chain of the next.
+template <int NPASS, int NB, int BN, int RES_KB, int AKB, int CL, bool PAIR = false, int SEL = 0, bool TB = false,
+          int SGT = 0>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     bmu_cand_tensor_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                            const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
@@ -428,6 +452,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   // fp32 sums) holds for any D.
   constexpr bool SEGM = PAIR && C::ASTREAM && BN == 128;
   constexpr int SEG = 4;
+  constexpr bool SEGT = SGT > 0;
+  static_assert(!SEGT || (PAIR && C::ASTREAM && BN == 256 && C::NACC == 2 && SEL == 0), "tensor-memory sums: streamed pair form, 256 columns");
   static_assert(!SEGM || BN / 32 == EPI_SUBS, "segmented accumulation: one chunk per epilogue warp and tile");
   constexpr bool PAIR_ATM = PAIR && ATM;  // (the streamed pair form keeps whole stages: prototypes half + samples)
   constexpr int SLOT_BYTES = PAIR_ATM ? A_TILE_BYTES : C::STAGE_BYTES;
@@ -649,6 +675,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       constexpr uint32_t idesc = instr_desc_f16(PAIR ? 2 * BM : BM, BN);
       int stage = 0;
       uint32_t phase = 0, a_phase = 0, acc = 0, acc_phase = 0;
+      uint32_t rph = 0;  // SEGT: phase bit of each tensor-memory region (acc = the sum region of the current tile)
       unsigned long long mask_next = SEL == 2 ? sel_mask(0) : 0ull;  // the pair's mask is loaded one row tile ahead
       for (int64_t it = 0; it < n_iters; ++it) {
         const unsigned long long mask_it = mask_next;
@@ -699,15 +726,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         const int n_sel = SEL == 2 ? __popcll(mask_it) : NT;
         for (int nt = 0; nt < n_sel; ++nt) {
           uint32_t tmem_d = tmem_base + acc * BN;
-          if (!SEGM) {
+          if (!SEGM && !SEGT) {
             mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
             tc_fence_after();
           }
+          uint32_t region = acc;
           for (int kb = 0; kb < KB; ++kb) {
             if (SEGM && kb % SEG == 0) {  // a fresh partial accumulator
               mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
               tc_fence_after();
               tmem_d = tmem_base + acc * BN;
+            }
+            if (SEGT && kb % (SEGT ? SGT : 1) == 0) {  // a fresh chain: into the sum region first, then into the other one
+              region = kb == 0 ? acc : acc ^ 1u;
+              mbar_wait(&bars->tmem_empty[region], ((rph >> region) & 1u) ^ 1u);
+              tc_fence_after();
+              tmem_d = tmem_base + region * BN;
             }
             mbar_wait(&bars->full[stage], phase);
             tc_fence_after();
@@ -722,7 +756,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
               const uint32_t koff = k * UMMA_K * 2;  // bytes along K inside the swizzle atom
               if (PAIR && ASTREAM) {  // both operands from shared memory, each CTA's own sample rows
                 tc_mma_f16_ss_pair(tmem_d, smem_desc_sw128(a_hi + koff), smem_desc_sw128(b_hi + koff), idesc,
-                                   ((SEGM ? kb % SEG : kb) | k) != 0);
+                                   ((SEGM ? kb % SEG : SEGT ? kb % (SEGT ? SGT : 1) : kb) | k) != 0);
                 if (NPASS == 3) {
                   tc_mma_f16_ss_pair(tmem_d, smem_desc_sw128(a_hi + koff), smem_desc_sw128(b_lo + koff), idesc, 1);
                   tc_mma_f16_ss_pair(tmem_d, smem_desc_sw128(a_lo + koff), smem_desc_sw128(b_hi + koff), idesc, 1);
@@ -758,6 +792,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
               stage = 0;
               phase ^= 1;
             }
+            if (SEGT && (kb % (SEGT ? SGT : 1) == (SEGT ? SGT : 1) - 1 || kb == KB - 1)) {  // chain complete
+              tc_commit_pair(&bars->tmem_full[region], cl_mask);
+              rph ^= 1u << region;
+            }
             if (SEGM && kb % SEG == SEG - 1 && kb != KB - 1) {  // partial accumulator complete (the last one below)
               tc_commit_pair(&bars->tmem_full[acc], cl_mask);
               if (++acc == NACC) {
@@ -778,7 +816,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             }
           }
           // accumulator complete -> epilogue (pair: of both CTAs)
-          if (PAIR) tc_commit_pair(&bars->tmem_full[acc], cl_mask); else tc_commit(&bars->tmem_full[acc]);
+          if (SEGT) {
+          } else if (PAIR) tc_commit_pair(&bars->tmem_full[acc], cl_mask); else tc_commit(&bars->tmem_full[acc]);
           if (++acc == NACC) {
             acc = 0;
             acc_phase ^= 1;
@@ -817,6 +856,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const float* wn_src = wn_in_smem ? wn_smem : wnorm;
     asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
     uint32_t acc = 0, acc_phase = 0;
+    uint32_t eph = 0;  // SEGT: phase bit of each tensor-memory region, epilogue side
+    (void)eph;
     if constexpr (SEL == 1) {
       // ------------------------------------------------------------ FLAG pass: lean epilogue, no candidate tables
       // Per 32-column chunk a thread (= sample row) forms its 32 one-pass scores and stores their minimum in shared
@@ -950,7 +991,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           const float xw = xn_row * um;
           kb = xw * bound_coef + acc_coef * (xw + wm);
         }
-        mbar_wait(&bars->tmem_full[acc], acc_phase);
+        if constexpr (SEGT) {
+          // sums in tensor memory: region `acc` holds the first chain of this tile, every later chain arrives in the
+          // other region and is added in (my chunks only), 16 columns at a time
+          const uint32_t R = acc, Q = acc ^ 1u;
+          mbar_wait(&bars->tmem_full[R], (eph >> R) & 1u);
+          eph ^= 1u << R;
+          const int nseg = (KB + SGT - 1) / SGT;
+          for (int sg = 1; sg < nseg; ++sg) {
+            mbar_wait(&bars->tmem_full[Q], (eph >> Q) & 1u);
+            eph ^= 1u << Q;
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = (sub - ti * CHUNKS) & (EPI_SUBS - 1); c < CHUNKS; c += EPI_SUBS) {
+              // all four loads of a chunk in flight together (the MMA stream waits for this region)
+              uint32_t p0[16], q0[16], p1[16], q1[16];
+              const uint32_t pa = tmem_base + lane_base + Q * BN + c * 32, qa = tmem_base + lane_base + R * BN + c * 32;
+              tmem_ld_32x16(pa, p0);
+              tmem_ld_32x16(qa, q0);
+              tmem_ld_32x16(pa + 16, p1);
+              tmem_ld_32x16(qa + 16, q1);
+              tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                q0[e] = __float_as_uint(__uint_as_float(q0[e]) + __uint_as_float(p0[e]));
+                q1[e] = __float_as_uint(__uint_as_float(q1[e]) + __uint_as_float(p1[e]));
+              }
+              tmem_st_32x16(qa, q0);
+              tmem_st_32x16(qa + 16, q1);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->tmem_empty[Q]), 0));
+          }
+        } else {
+          mbar_wait(&bars->tmem_full[acc], acc_phase);
+        }
         tc_fence_after();
         const uint32_t tmem_acc = tmem_base + lane_base + acc * BN;
         // every fourth chunk (counted over the whole row tile) is mine: start at it instead of testing each one
@@ -1236,7 +1313,7 @@ int sm_count() {
   return n;
 }
 
-template <int NPASS, int NB, int BN, int RES_KB, int AKB, int CL, bool PAIR = false, int SEL = 0, bool TB = false>
+template <int NPASS, int NB, int BN, int RES_KB, int AKB, int CL, bool PAIR = false, int SEL = 0, bool TB = false, int SGT = 0>
 int launch_cfg_cl(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t s) {
   using C = Cfg<NPASS, BN, RES_KB, AKB, PAIR && AKB == 0 && RES_KB == 0, SEL == 1 ? kFlagChunkBytes : 0>;
   CUtensorMap mxh, mxl, mwh, mwl;
@@ -1268,7 +1345,7 @@ int launch_cfg_cl(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t
       fprintf(stderr, "dbgsom: K1 takes wnorm through the bias k-step, E = %g\n", e);
     }
   }
-  auto kern = bmu_cand_tensor_kernel<NPASS, NB, BN, RES_KB, AKB, CL, PAIR, SEL, TB>;
+  auto kern = bmu_cand_tensor_kernel<NPASS, NB, BN, RES_KB, AKB, CL, PAIR, SEL, TB, SGT>;
   DBGSOM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   const int KB = (int)(a.ld16 / BK);
   const int NT = a.Mpad / BN;  // prototypes are permuted over all Mpad shadow rows
@@ -1352,9 +1429,18 @@ bool streamed_pairs(const dbgsom_bmu_args& a) {
   return a.backend == DBGSOM_BMU_TENSOR && a.n_pass == 3 && a.ld16 / BK > MAX_RES_KB && pairs && cluster_size() >= 2 &&
          ceil_div<int64_t>(a.N, BM) >= sm_count();
 }
-bool streamed_segmented(const dbgsom_bmu_args& a) {
-  static const bool segm = getenv("DBGSOM_TC_SEGM") == nullptr || atoi(getenv("DBGSOM_TC_SEGM")) != 0;
-  return segm && streamed_pairs(a);
+// DBGSOM_TC_SEGM: 3 (default) / 2 = segmented accumulation with 256-column MMAs and the running sums in tensor memory,
+// chains of 4 / 8 k-blocks; 1 = segmented accumulation with 128-column MMAs, running sums in registers (the first
+// segmented form: same bound as 3, but HBM bound on re-streamed sample tiles); 0 = one chain, 256-column MMAs.
+// Config-5 shard (625k x 4096 rows, 16384 prototypes), candidate search per epoch: 221 / 212 / 289 / 193 ms.
+int streamed_segm_mode() {
+  static const int mode = getenv("DBGSOM_TC_SEGM") == nullptr ? 3 : atoi(getenv("DBGSOM_TC_SEGM"));
+  return mode;
+}
+bool streamed_segmented(const dbgsom_bmu_args& a) { return streamed_segm_mode() == 1 && streamed_pairs(a); }
+int streamed_tmem_sums(const dbgsom_bmu_args& a) {  // k-blocks per chain, 0 = another form
+  const int mode = streamed_segm_mode();
+  return (mode == 2 || mode == 3) && streamed_pairs(a) ? (mode == 2 ? 8 : 4) : 0;
 }
 }  // namespace
 // per-tile error bounds (template flag TB): the streamed pair forms, one winner, the caller supplied the tile maxima
@@ -1380,15 +1466,21 @@ int launch_shape(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t 
     // D > 256: both operands stream.  As CTA pairs with 256-column MMAs each CTA stages its 128 sample rows and HALF
     // of a 256-prototype tile per k-block (the single-CTA form wants 208 B/clk from the shared-memory pipe, this 104)
     if (streamed_pairs(a)) {
-      // segmented accumulation (128-column tiles, partial accumulators summed in the epilogue) keeps the error bound
-      // of D = 256 at any D; DBGSOM_TC_SEGM=0 selects the one-chain form with 256-column tiles
+      // segmented accumulation (chains of four k-blocks; 256-column tiles with the running sums in tensor memory, or
+      // 128-column tiles with the sums in registers) keeps the error bound of D = 256 at any D; DBGSOM_TC_SEGM=0
+      // selects the one-chain form with 256-column tiles
+      const int sgt = streamed_tmem_sums(a);
       if constexpr (NB == 1) {
         if (tile_bounds_active(a)) {
           if (streamed_segmented(a)) return launch_cfg_cl<NPASS, NB, 128, 0, 0, 2, true, 0, true>(a, ws, s);
+          if (sgt == 8) return launch_cfg_cl<NPASS, NB, 256, 0, 0, 2, true, 0, true, 8>(a, ws, s);
+          if (sgt == 4) return launch_cfg_cl<NPASS, NB, 256, 0, 0, 2, true, 0, true, 4>(a, ws, s);
           return launch_cfg_cl<NPASS, NB, 256, 0, 0, 2, true, 0, true>(a, ws, s);
         }
       }
       if (streamed_segmented(a)) return launch_cfg_cl<NPASS, NB, 128, 0, 0, 2, true>(a, ws, s);
+      if (sgt == 8) return launch_cfg_cl<NPASS, NB, 256, 0, 0, 2, true, 0, false, 8>(a, ws, s);
+      if (sgt == 4) return launch_cfg_cl<NPASS, NB, 256, 0, 0, 2, true, 0, false, 4>(a, ws, s);
       return launch_cfg_cl<NPASS, NB, 256, 0, 0, 2, true>(a, ws, s);
     }
     return launch_cfg<NPASS, NB, 128, 0>(a, ws, s);
@@ -1400,6 +1492,12 @@ int launch_shape(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t 
 float tensor_acc_coef_args(const dbgsom_bmu_args& a) {
   if (streamed_segmented(a)) {  // chains of 48 steps like D = 256, plus the fp32 sums of the partial tiles
     double c = 2.4e-7 * (a.strict ? 4.0 : 2.0);
+    if (const char* e = getenv("DBGSOM_ACC_SCALE")) c *= atof(e);
+    return (float)c;
+  }
+  if (const int sgt = streamed_tmem_sums(a)) {  // chains of 12 * sgt steps (48 at four k-blocks), plus the fp32 sums
+    const double grow = (double)sgt / 4.0;
+    double c = 2.4e-7 * (a.strict ? 4.0 * grow : 2.0 * sqrt(grow));
     if (const char* e = getenv("DBGSOM_ACC_SCALE")) c *= atof(e);
     return (float)c;
   }

@@ -726,6 +726,8 @@ def test_tile_bounds_are_the_column_tile_maxima():
     ({"DBGSOM_TC_PAIR": "1", "DBGSOM_TC_BIAS": "1"}, ("60000", "128", "1024", "4")),
     ({"DBGSOM_TC_PAIR": "1"}, ("60000", "512", "1024", "3")),
     ({"DBGSOM_TC_PAIR": "1", "DBGSOM_TC_SEGM": "0"}, ("60000", "512", "1024", "3")),
+    ({"DBGSOM_TC_SEGM": "1"}, ("60000", "512", "1024", "3")),
+    ({"DBGSOM_TC_SEGM": "2"}, ("40000", "2048", "4096", "4")),
     ({"DBGSOM_TC_PAIR": "0"}, ("60000", "512", "1024", "3")),
     # 768 accumulation steps per score at D = 4096: wrong winners with exact relative gaps up to 8e-6 with the bound of
     # D = 256; now the chain is cut into partial accumulators (segmented form), or the bound follows the chain
@@ -737,11 +739,13 @@ def test_tile_bounds_are_the_column_tile_maxima():
     ({}, ("40000", "2048", "4096", "6")),
     ({"DBGSOM_TC_SEGM": "0"}, ("40000", "2048", "4096", "6")),
 ], ids=["multicast-cluster", "single-cta", "cta-pair", "cta-pair-bias-kstep", "cta-pair-streamed-segmented",
-        "cta-pair-streamed-one-chain", "multicast-streamed", "long-accumulation-chain", "streamed-map-wide-bound",
+        "cta-pair-streamed-one-chain", "cta-pair-streamed-segmented-register-sums", "cta-pair-streamed-segmented-8-kblocks",
+        "multicast-streamed", "long-accumulation-chain", "streamed-map-wide-bound",
         "tile-bounds-flat-sheet-segmented", "tile-bounds-flat-sheet-one-chain"])
 def test_tensor_kernel_variants_agree_with_simt(env, shape):
     """The forms of the tcgen05 candidate kernel (CTA pairs with cta_group::2 -- the default; sample tile in tensor
-    memory for D <= 256, both operands streamed beyond; optionally wnorm as a bias k-step --, clusters with TMA
+    memory for D <= 256, both operands streamed beyond, there with segmented accumulation whose running sums live in
+    tensor memory -- the default -- or in registers, or with one accumulation chain; optionally wnorm as a bias k-step --, clusters with TMA
     multicast, single CTAs) are selected by environment switches read once per process, so each runs in its own
     interpreter: winners on a four-epoch bench-like trajectory must equal the fp32 SIMT back end's
     (both followed by the exact float64 re-score) outside a 1e-7 relative float64 gap."""

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--n-iter", type=int, default=200)
     ap.add_argument("--max-neurons", type=int, default=16384)
     ap.add_argument("--spreading-factor", type=float, default=0.999)
+    ap.add_argument("--coarse-frac", type=float, default=0.5, help="share of the epochs in the coarse (growing) phase")
     ap.add_argument("--manifold", action="store_true", help="noisy 2-D sheet instead of the Gaussian mixture")
     ap.add_argument("--aligned", action="store_true", help="index-aligned centre rows instead of the reference's packing")
     ap.add_argument("--distributed", action="store_true", help="one rank per GPU under torchrun; --n rows per rank")
@@ -64,7 +65,8 @@ def main():
 
     SomVQ(max_neurons=8, n_iter=3, random_state=0, device=device).fit(X[:2000])  # warm up CUDA context / library
     est = SomVQ(max_neurons=args.max_neurons, n_iter=args.n_iter, random_state=0, spreading_factor=args.spreading_factor,
-                compat_pack_rows=not args.aligned, verbose=rank == 0, device=device, distributed=args.distributed)
+                compat_pack_rows=not args.aligned, verbose=rank == 0, device=device, distributed=args.distributed,
+                coarse_training_frac=args.coarse_frac)
     if args.distributed:
         dist.barrier()
     t0 = time.perf_counter()
@@ -85,7 +87,7 @@ def main():
         if args.json:
             import json
 
-            rec = {"tool": "fit_config5", "gpus": world, "rows_total": rows_total, "d": args.d, "epochs": int(epochs),
+            rec = {"tool": "fit_config5", "gpus": world, "rows_total": rows_total, "d": args.d, "epochs": int(epochs), "coarse_training_frac": args.coarse_frac,
                    "fit_s": dt, "epochs_per_s": epochs / dt, "samples_per_s_per_epoch": rows_total * epochs / dt,
                    "neurons_grown_to": grown, "neurons_after_pruning": len(est.neurons_), "max_neurons": args.max_neurons,
                    "data": "noisy 2-D sheet in D dimensions" if args.manifold else "Gaussian mixture",

@@ -211,7 +211,7 @@ __device__ __forceinline__ double f32_as_f64(float f) {
 // instructions per 4-row batch were loop control.
 // All arithmetic is float64: distances by direct differences, k = 1 - sqrt(1 - exp(-d^2 / V))
 // literally as dbgsom/BaseSom.py:536-537, sums in float64 registers.
-template <int VPL, int WPR, int U, int THREADS, int STAGES, bool FULLD, bool XU2>
+template <int VPL, int WPR, int U, int THREADS, int STAGES, bool FULLD, int XU>
 __global__ void __launch_bounds__(THREADS, 2) accumulate_kernel(
     const float* __restrict__ X, int64_t N, int D, int64_t ldx, const int32_t* __restrict__ perm,
     const int32_t* __restrict__ offsets, const double* __restrict__ W, int M, double inv_var,
@@ -382,12 +382,12 @@ __global__ void __launch_bounds__(THREADS, 2) accumulate_kernel(
               asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
                            : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
                            : "r"(rows + (u * VPL + v) * 512));
-              // one or two conversions in four go through the XU pipe (F2F, ~27 clk per warp instruction,
-              // otherwise idle), the rest through the ALU/FMA pipes: neither saturates
+              // XU of the four conversions go through the XU pipe (F2F.F64.F32, otherwise idle), the rest through the
+              // ALU / FMA pipes (four integer instructions each)
               xd[u][v][0] = (double)x.x;
-              xd[u][v][1] = f32_as_f64(x.y);
-              xd[u][v][2] = XU2 ? (double)x.z : f32_as_f64(x.z);
-              xd[u][v][3] = f32_as_f64(x.w);
+              xd[u][v][1] = XU >= 3 ? (double)x.y : f32_as_f64(x.y);
+              xd[u][v][2] = XU >= 2 ? (double)x.z : f32_as_f64(x.z);
+              xd[u][v][3] = XU >= 4 ? (double)x.w : f32_as_f64(x.w);
             }
           }
           // the prototype's columns are read once per batch and used for all its rows
@@ -450,7 +450,7 @@ __global__ void __launch_bounds__(THREADS, 2) accumulate_kernel(
   if (seg >= 0) flush();
 }
 
-template <int VPL, int WPR, int U, bool XU2 = false>
+template <int VPL, int WPR, int U, int XU = 1>
 int launch_accumulate(const dbgsom_accumulate_args& a, const int32_t* perm, const int32_t* offsets, cudaStream_t s) {
   // one warp per row (WPR = 1): 6 warps per CTA leave 168 registers per thread at two CTAs per SM, enough
   // for the U * VPL * 4 converted elements + prototype + sums without spilling (at 128 registers the
@@ -459,8 +459,8 @@ int launch_accumulate(const dbgsom_accumulate_args& a, const int32_t* perm, cons
   constexpr int STAGES = WPR == 1 ? 4 : 3;
   constexpr int TEAMS = THREADS / 32 / WPR;
   const size_t smem = (size_t)(THREADS / 32) * (STAGES * U * VPL * 512 + VPL * 1024 + ACC_WIN_BYTES);
-  auto kern = a.D == 128 * VPL * WPR ? accumulate_kernel<VPL, WPR, U, THREADS, STAGES, true, XU2>
-                                     : accumulate_kernel<VPL, WPR, U, THREADS, STAGES, false, XU2>;
+  auto kern = a.D == 128 * VPL * WPR ? accumulate_kernel<VPL, WPR, U, THREADS, STAGES, true, XU>
+                                     : accumulate_kernel<VPL, WPR, U, THREADS, STAGES, false, XU>;
   DBGSOM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;  // resident CTAs per SM: 2 by registers (__launch_bounds__) if the staging rings fit twice
   DBGSOM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
@@ -544,18 +544,24 @@ int run_accumulate(const dbgsom_accumulate_args& a, cudaStream_t s) {
   const int D4 = a.D;
   static const char* tune_u = getenv("DBGSOM_ACC_ROWS");  // tuning switch: rows per batch for D <= 256
   const int u_small = tune_u ? atoi(tune_u) : 0;
-  // two float -> double conversions in four on the XU pipe (default; DBGSOM_ACC_XU2=0: one in four).  With the lean
-  // loop control the kernel has XU cycles to spare: 10M x 256 rows 1.80 -> 1.72 ms, 12.5M x 128 rows 1.33 -> 1.30 ms
-  static const char* tune_xu = getenv("DBGSOM_ACC_XU2");
-  const bool xu2 = !tune_xu || atoi(tune_xu) != 0;
+  // float -> double conversions on the XU pipe (F2F) per float4; the rest take four integer instructions each on the
+  // ALU / FMA pipes.  Default: all four -- with the lean loop control the kernel is short of issue slots, not of XU
+  // cycles (ncu: XU 20 % busy at two in four).  10M x 256 rows stand-alone 1.80 (one) / 1.76 (two) / 1.72 ms (four);
+  // in the bench epoch, at the clock K1 leaves, 2.21 / 2.17 / 2.12 ms.  DBGSOM_ACC_XU=1..4 selects.
+  static const char* tune_xu = getenv("DBGSOM_ACC_XU");
+  const int xu = tune_xu ? atoi(tune_xu) : 4;
   if (D4 <= 128) {
     if (u_small == 4) return launch_accumulate<1, 1, 4>(a, ws.perm, ws.offsets, s);
-    if (xu2) return launch_accumulate<1, 1, 8, true>(a, ws.perm, ws.offsets, s);
+    if (xu >= 4) return launch_accumulate<1, 1, 8, 4>(a, ws.perm, ws.offsets, s);
+    if (xu == 3) return launch_accumulate<1, 1, 8, 3>(a, ws.perm, ws.offsets, s);
+    if (xu == 2) return launch_accumulate<1, 1, 8, 2>(a, ws.perm, ws.offsets, s);
     return launch_accumulate<1, 1, 8>(a, ws.perm, ws.offsets, s);
   }
   if (D4 <= 256) {
     if (u_small == 2) return launch_accumulate<2, 1, 2>(a, ws.perm, ws.offsets, s);
-    if (xu2) return launch_accumulate<2, 1, 4, true>(a, ws.perm, ws.offsets, s);
+    if (xu >= 4) return launch_accumulate<2, 1, 4, 4>(a, ws.perm, ws.offsets, s);
+    if (xu == 3) return launch_accumulate<2, 1, 4, 3>(a, ws.perm, ws.offsets, s);
+    if (xu == 2) return launch_accumulate<2, 1, 4, 2>(a, ws.perm, ws.offsets, s);
     return launch_accumulate<2, 1, 4>(a, ws.perm, ws.offsets, s);
   }
   if (D4 <= 512) return launch_accumulate<4, 1, 2>(a, ws.perm, ws.offsets, s);

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256) denominator_kernel(const uint16_t* __rest
 // 16-wide steps over the live list, 8 x 4 outputs per thread (6 shared-memory vector loads per 32 DFMA keeps
 // the float64 pipe, not the LDS port, the limiter).
 constexpr int TI = 128, TD = 64, TJ = 16;
-__global__ void __launch_bounds__(256) smooth_gemm_kernel(const uint16_t* __restrict__ hop, int64_t ldh,
+__global__ void __launch_bounds__(256, 2) smooth_gemm_kernel(const uint16_t* __restrict__ hop, int64_t ldh,
                                                          const double* __restrict__ lut, int lut_len,
                                                          const double* __restrict__ B, const double* __restrict__ den,
                                                          const int32_t* __restrict__ live,
@@ -120,31 +120,42 @@ __global__ void __launch_bounds__(256) smooth_gemm_kernel(const uint16_t* __rest
   const int L = *n_live;
   double acc[8][4] = {};
 
-  for (int j0 = 0; j0 < L; j0 += TJ) {
-    // H tile: 128 x 16 entries, 8 per thread: thread -> (i = tid / 2, 8 consecutive j)
-    {
-      const int ii = tid >> 1, jj = (tid & 1) * 8;
-      const int i = i0 + ii;
+  // Software pipeline: the next step's H entries (hop -> table lookup: two dependent loads) and B entries are fetched
+  // into registers while the current step is computed from shared memory; the first version loaded, synchronised,
+  // computed and synchronised again, with the global-load latency exposed once per 16 live neurons (~35 % of the
+  // float64 pipe).
+  const int ii = tid >> 1, jj0 = (tid & 1) * 8;  // H tile: thread -> (i = tid / 2, 8 consecutive j)
+  const int hi_row = i0 + ii;
+  double hq[8], bq[4];
+  auto fetch = [&](int j0) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int j = j0 + jj + q;
-        double h = 0.0;
-        if (i < row_end && j < L) {
-          const unsigned hp = hop[(int64_t)i * ldh + live[j]];
-          if (hp < (unsigned)lut_len) h = lut[hp];
-        }
-        Hs[jj + q][ii] = h;
+    for (int q = 0; q < 8; ++q) {
+      const int j = j0 + jj0 + q;
+      double h = 0.0;
+      if (hi_row < row_end && j < L) {
+        const unsigned hp = hop[(int64_t)hi_row * ldh + live[j]];
+        if (hp < (unsigned)lut_len) h = lut[hp];
       }
+      hq[q] = h;
     }
-    // B tile: 16 x 64 doubles, 4 per thread
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int e = tid + q * 256;
-      const int jj = e / TD, dd = e % TD;
-      const int j = j0 + jj, d = d0 + dd;
-      Bs[jj][dd] = (j < L && d < D) ? B[(int64_t)j * D + d] : 0.0;
+      const int j = j0 + e / TD, d = d0 + e % TD;
+      bq[q] = (j < L && d < D) ? B[(int64_t)j * D + d] : 0.0;
+    }
+  };
+  if (L > 0) fetch(0);
+  for (int j0 = 0; j0 < L; j0 += TJ) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) Hs[jj0 + q][ii] = hq[q];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e = tid + q * 256;
+      Bs[e / TD][e % TD] = bq[q];
     }
     __syncthreads();
+    if (j0 + TJ < L) fetch(j0 + TJ);
 #pragma unroll
     for (int jj = 0; jj < TJ; ++jj) {
       double h[8];

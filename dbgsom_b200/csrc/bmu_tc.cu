@@ -1012,6 +1012,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
               tmem_ld_32x16(pa + 16, p1);
               tmem_ld_32x16(qa + 16, q1);
               tmem_ld_wait();
+              if (c + EPI_SUBS >= CHUNKS) {
+                // my last chunk of the partial is in registers: hand the region back before the add and the stores
+                // (they touch the sum region only), ~150 cycles earlier on the MMA stream's critical path
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->tmem_empty[Q]), 0));
+              }
 #pragma unroll
               for (int e = 0; e < 16; ++e) {
                 q0[e] = __float_as_uint(__uint_as_float(q0[e]) + __uint_as_float(p0[e]));
@@ -1021,9 +1028,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
               tmem_st_32x16(qa + 16, q1);
             }
             tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->tmem_empty[Q]), 0));
           }
         } else {
           mbar_wait(&bars->tmem_full[acc], acc_phase);

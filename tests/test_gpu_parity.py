@@ -382,14 +382,18 @@ def test_epoch_wide_rows_and_large_maps(shape):
 
 
 @pytest.mark.parametrize("shape,backend", [((200_000, 256, 64), "tensor"), ((70_000, 784, 20), "auto"),
-                                            ((120_000, 128, 64), "tensor")],
-                         ids=["c3-shape-200k-x256-m4096", "c2-shape-70k-x784-m400", "c4-shape-120k-x128-m4096"])
+                                            ((120_000, 128, 64), "tensor"), ((19_200, 4096, 64), "tensor")],
+                         ids=["c3-shape-200k-x256-m4096", "c2-shape-70k-x784-m400", "c4-shape-120k-x128-m4096",
+                              "c5-width-19k-x4096-m4096"])
 def test_epoch_parity_over_a_trajectory_at_baseline_shapes(shape, backend):
     """Oracle parity of EVERY epoch output at the BASELINE feature widths and map sizes (configs 3, 2 and 4 at a row
     count the float64 oracle finishes in seconds), over six consecutive epochs of the real training trajectory:
     random-row prototypes first, then the smooth, partly dead maps of the large-sigma phase, where the packed-row
     quirk (Q1) is active.  Each epoch starts from the DEVICE's prototypes, so errors cannot hide by accumulating
-    in the oracle's favour, and the oracle update is teacher-forced only on the exempt near-tie samples."""
+    in the oracle's favour, and the oracle update is teacher-forced only on the exempt near-tie samples.
+    The config-5 width (D = 4096, 150 row tiles: the streamed CTA-pair search with segmented accumulation in tensor
+    memory and per-tile error bounds) runs on a 64 x 64 map; its half-trained maps are the flat sheets on which
+    thousands of prototypes tie."""
     from bench import sigma_at
 
     n, d, side = shape
@@ -422,7 +426,7 @@ def test_epoch_parity_over_a_trajectory_at_baseline_shapes(shape, backend):
         # (the ten-component config-2 mixture on a 400-neuron map collapses much further: most samples there sit
         # between prototypes that agree to 1e-6)
         n_strict, _, ref = assert_epoch_parity(r, e.weights(), X, W, hop, sigma, stats["total_variance"],
-                                               min_strict=0.85 if d != 784 else 0.2)
+                                               min_strict=0.85 if d not in (784, 4096) else 0.2)
         compared += n_strict
         live = np.flatnonzero(ref["n"] > 0)
         dead = np.flatnonzero(ref["n"] == 0)
@@ -437,7 +441,7 @@ def test_epoch_parity_over_a_trajectory_at_baseline_shapes(shape, backend):
         assert st["selective_searches"] == n_epochs - 1 and st["classic_searches"] == 1
         assert 0.0 < st["refined_share"] < 0.9
     e.close()
-    assert compared > (0.9 if d != 784 else 0.3) * n_epochs * n
+    assert compared > (0.9 if d not in (784, 4096) else 0.3) * n_epochs * n
     assert dead_below_live >= 1, "the trajectory should exercise the packed-row quirk"
 
 

@@ -885,23 +885,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           for (int c = (sub - nt * CHUNKS) & (EPI_SUBS - 1); c < CHUNKS; c += EPI_SUBS) {
             uint32_t r[32];
             tmem_ld_32x32(tmem_acc + c * 32, r);
-            const int col = nt * BN + c * 32;
-            const float4* wn4 = reinterpret_cast<const float4*>(wn_src + col);
-            float4 w4[8];
+            float a1;
+            if (bias_mode) {
+              // wnorm came in through the bias k-step: the accumulator is -score / 2, so the chunk's smallest score is
+              // -2 x its largest accumulator -- no per-column load, no FFMA (at D = 128 this epilogue, not the MMA
+              // stream, set the pace of the FLAG pass)
+              tmem_ld_wait();
+              float gmx[8];
 #pragma unroll
-            for (int g = 0; g < 8; ++g) w4[g] = wn4[g];
-            tmem_ld_wait();
-            float gmn[8];
+              for (int g = 0; g < 8; ++g)
+                gmx[g] = fmaxf(fmaxf(__uint_as_float(r[4 * g + 0]), __uint_as_float(r[4 * g + 1])),
+                               fmaxf(__uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3])));
+              a1 = -2.f * fmaxf(fmaxf(fmaxf(gmx[0], gmx[1]), fmaxf(gmx[2], gmx[3])),
+                                fmaxf(fmaxf(gmx[4], gmx[5]), fmaxf(gmx[6], gmx[7])));
+            } else {
+              const int col = nt * BN + c * 32;
+              const float4* wn4 = reinterpret_cast<const float4*>(wn_src + col);
+              float4 w4[8];
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const float s0 = fmaf(-2.f, __uint_as_float(r[4 * g + 0]), w4[g].x);
-              const float s1 = fmaf(-2.f, __uint_as_float(r[4 * g + 1]), w4[g].y);
-              const float s2 = fmaf(-2.f, __uint_as_float(r[4 * g + 2]), w4[g].z);
-              const float s3 = fmaf(-2.f, __uint_as_float(r[4 * g + 3]), w4[g].w);
-              gmn[g] = fminf(fminf(s0, s1), fminf(s2, s3));
+              for (int g = 0; g < 8; ++g) w4[g] = wn4[g];
+              tmem_ld_wait();
+              float gmn[8];
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const float s0 = fmaf(-2.f, __uint_as_float(r[4 * g + 0]), w4[g].x);
+                const float s1 = fmaf(-2.f, __uint_as_float(r[4 * g + 1]), w4[g].y);
+                const float s2 = fmaf(-2.f, __uint_as_float(r[4 * g + 2]), w4[g].z);
+                const float s3 = fmaf(-2.f, __uint_as_float(r[4 * g + 3]), w4[g].w);
+                gmn[g] = fminf(fminf(s0, s1), fminf(s2, s3));
+              }
+              a1 = fminf(fminf(fminf(gmn[0], gmn[1]), fminf(gmn[2], gmn[3])),
+                         fminf(fminf(gmn[4], gmn[5]), fminf(gmn[6], gmn[7])));
             }
-            const float a1 = fminf(fminf(fminf(gmn[0], gmn[1]), fminf(gmn[2], gmn[3])),
-                                   fminf(fminf(gmn[4], gmn[5]), fminf(gmn[6], gmn[7])));
             chunk_min[(nt * CHUNKS + c) * BM + t] = a1;
             m1 = fminf(m1, a1);
           }
@@ -1335,7 +1350,8 @@ int launch_cfg_cl(const dbgsom_bmu_args& a, const BmuWorkspace& ws, cudaStream_t
     mwl = mwh;
   }
   CUtensorMap mwb = mwh;
-  const bool with_bias = SEL == 0 && PAIR && C::ATM && a.d_Wb16 != nullptr && a.d_bias_scale != nullptr;
+  // (the classic search, and the FLAG pass of the selective search for D <= 128, where its epilogue is the limiter)
+  const bool with_bias = (SEL == 0 || (SEL == 1 && AKB <= 2)) && PAIR && C::ATM && a.d_Wb16 != nullptr && a.d_bias_scale != nullptr;
   if (with_bias) {
     rc = make_map(&mwb, a.d_Wb16, a.Mpad, BK, BN / CL);
     if (rc) return rc;

@@ -565,14 +565,21 @@ class DeviceEngine:
         # experiment, off by default: wnorm enters the accumulator through an extra k-step (dbgsom_prepare_bias).  It
         # halves the epilogue's shared-memory loads but measured no gain (D = 256: MMA bound; D = 128: the epilogue is
         # bound by its instruction count, not by the shared-memory pipe) -- see DESIGN.md, K1.
-        if tensor and need_lo and os.environ.get("DBGSOM_TC_BIAS", "0") == "1":
+        # DBGSOM_FLAG_BIAS=1 (off by default) uses it in the FLAG pass of the selective search for D <= 128, whose lean
+        # epilogue then needs no per-column load and no FFMA: 12.5M x 128 rows 11.83 -> 11.36 ms (the pass becomes MMA
+        # bound including the extra k-step), epoch 21.0 -> 20.7 ms; winners unchanged (c4-shape trajectory test)
+        flag_bias = bool(tensor and need_lo and top1 and map_order and not tile and self.ld16 <= 128
+                         and os.environ.get("DBGSOM_FLAG_BIAS", "0") == "1")
+        self._flag_bias_ready = False
+        if flag_bias or (tensor and need_lo and os.environ.get("DBGSOM_TC_BIAS", "0") == "1"):
             nat.check(
                 self.lib.dbgsom_prepare_bias(self.wnorm.data_ptr(), mpad, self.wmax.data_ptr(), self.Wb16.data_ptr(),
                                              self.bias_scale.data_ptr(), self._stream()),
                 "dbgsom_prepare_bias",
             )
             self.launches += 1
-            self._bias_ready = True
+            self._bias_ready = os.environ.get("DBGSOM_TC_BIAS", "0") == "1"
+            self._flag_bias_ready = flag_bias
         else:
             self._bias_ready = False
         return mpad
@@ -642,8 +649,11 @@ class DeviceEngine:
             a.d_tile_mask = self.tile_mask.data_ptr()
             a.select_granule = self.select_granule
             a.select, a.n_pass = nat.SELECT_FLAG, 1
+            if getattr(self, "_flag_bias_ready", False):
+                a.d_Wb16, a.d_bias_scale = self.Wb16.data_ptr(), self.bias_scale.data_ptr()
             with self._Phase(self, "bmu_candidates"):
                 nat.check(self.lib.dbgsom_bmu_candidates(a, self._stream()), "dbgsom_bmu_candidates[flag]")
+            a.d_Wb16, a.d_bias_scale = None, None
             a.select, a.n_pass = nat.SELECT_REFINE, 3
             with self._Phase(self, "bmu_second_stage"):
                 nat.check(self.lib.dbgsom_bmu_candidates(a, self._stream()), "dbgsom_bmu_candidates[refine]")

@@ -173,7 +173,8 @@ typedef struct dbgsom_bmu_args {
   const uint16_t* d_W16_hi; /* [Mpad, ld16]; may be NULL for DBGSOM_BMU_SIMT */
   const uint16_t* d_W16_lo; /* [Mpad, ld16]; needed for n_pass = 3 */
   const float* d_wnorm;    /* [Mpad]; may be NULL for DBGSOM_BMU_SIMT */
-  const uint16_t* d_Wb16;  /* [Mpad, 64] from dbgsom_prepare_bias, or NULL */
+  const uint16_t* d_Wb16;  /* [Mpad, 64] from dbgsom_prepare_bias, or NULL (used by the classic CTA-pair search for
+                              D <= 256 and by the FLAG pass of the selective search for D <= 128) */
   const float* d_bias_scale; /* [1] from dbgsom_prepare_bias, or NULL */
   const float* d_wmax;     /* [4] from dbgsom_prepare_w */
   const int32_t* d_proto_of_col; /* [Mpad] prototype index stored in shadow row c (tensor back end;

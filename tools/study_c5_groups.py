@@ -112,7 +112,6 @@ def tile_bounds(order, tile=128, floor=0.125):
     wn_t = wn.view(-1, tile).max(1).values.clamp_min(floor * wn.max())
     um_c = um_t.repeat_interleave(tile)[: len(order)]
     wn_c = wn_t.repeat_interleave(tile)[: len(order)]
-    Bc = torch.empty(m, dtype=torch.float64, device=dev)  # per prototype coefficients
     um_p = torch.empty(m, dtype=torch.float64, device=dev)
     wn_p = torch.empty(m, dtype=torch.float64, device=dev)
     um_p[order] = um_c

@@ -1,4 +1,4 @@
-"""Executable model of the loop control of K2's accumulate kernel (dbgsom_b200/csrc/accumulate.cu, fourth version).
+"""Executable models of two pieces of kernel control logic: the loop control of K2's accumulate kernel (dbgsom_b200/csrc/accumulate.cu, fourth version) and, at the end of the file, the tensor-memory hand-over of the streamed BMU search.
 
 The kernel's control state is small enough to restate exactly: a prefetch cursor that cuts the sorted sample sequence
 into batches (never across a segment boundary), a 64-slot ring of row offsets with slots 0-7 mirrored behind the end,
@@ -116,3 +116,89 @@ def test_every_position_once_in_order_with_its_segment(U, STAGES):
         assert len(seen) == total
         seg_of = np.repeat(np.arange(M), counts)
         assert [s for _, s in seen] == seg_of.tolist()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The tensor-memory hand-over of the streamed BMU search (dbgsom_b200/csrc/bmu_tc.cu, SGT > 0): two 256-column regions
+# alternate as sum and partial accumulator, guarded by one full / empty mbarrier pair per region and per-region phase
+# bits on both sides.  Model: the MMA thread and the epilogue (all its warps move in lock step here) as coroutines over
+# mbarriers with the hardware's parity semantics; checked: no deadlock, the MMA stream never overwrites a region whose
+# contents are still needed, every tile's final sum holds each of its chains exactly once.
+class _Mbar:
+    def __init__(self):
+        self.phase = 0  # parity of the phase in progress
+
+    def done(self, parity):  # try_wait.parity: has the phase with this parity completed?
+        return self.phase != parity
+
+    def complete(self):
+        self.phase ^= 1
+
+
+def _run_hand_over(n_tiles, nseg):
+    full, empty = [_Mbar(), _Mbar()], [_Mbar(), _Mbar()]
+    region = [None, None]  # contents: None | ("chain", tile, seg) | ("sum", tile, {segs})
+    sums = {}
+
+    def mma():
+        acc, rph = 0, 0
+        for t in range(n_tiles):
+            for sg in range(nseg):
+                reg = acc if sg == 0 else acc ^ 1
+                while not empty[reg].done(((rph >> reg) & 1) ^ 1):
+                    yield
+                assert region[reg] is None, f"tile {t} chain {sg} overwrites {region[reg]}"
+                region[reg] = ("chain", t, sg)
+                yield  # the chain's MMAs run
+                full[reg].complete()  # tcgen05.commit
+                rph ^= 1 << reg
+            acc ^= 1
+
+    def epilogue():
+        acc, eph = 0, 0
+        for t in range(n_tiles):
+            R, Q = acc, acc ^ 1
+            while not full[R].done((eph >> R) & 1):
+                yield
+            eph ^= 1 << R
+            assert region[R] == ("chain", t, 0)
+            region[R] = ("sum", t, {0})
+            for sg in range(1, nseg):
+                while not full[Q].done((eph >> Q) & 1):
+                    yield
+                eph ^= 1 << Q
+                assert region[Q] == ("chain", t, sg)
+                assert sg not in region[R][2]
+                region[R][2].add(sg)
+                region[Q] = None
+                empty[Q].complete()  # all epilogue warps of both CTAs have arrived
+                yield
+            sums[t] = set(region[R][2])
+            region[R] = None
+            empty[R].complete()
+            acc ^= 1
+            yield
+
+    actors = [mma(), epilogue()]
+    alive = [True, True]
+    idle_rounds = 0
+    while any(alive):
+        before = (full[0].phase, full[1].phase, empty[0].phase, empty[1].phase, repr(region))
+        for i, a in enumerate(actors):
+            if alive[i]:
+                try:
+                    next(a)
+                except StopIteration:
+                    alive[i] = False
+        after = (full[0].phase, full[1].phase, empty[0].phase, empty[1].phase, repr(region))
+        idle_rounds = idle_rounds + 1 if before == after else 0
+        assert idle_rounds < 8, "deadlock: neither side makes progress"
+    return sums
+
+
+@pytest.mark.parametrize("nseg", [2, 3, 4, 8, 16])
+def test_tensor_memory_regions_alternate_without_deadlock(nseg):
+    for n_tiles in (1, 2, 3, 7):
+        sums = _run_hand_over(n_tiles, nseg)
+        assert sorted(sums) == list(range(n_tiles))
+        assert all(s == set(range(nseg)) for s in sums.values())
